@@ -1,0 +1,131 @@
+/*
+ * pf_b200.h -- C ABI of libpf_b200.so: the B200-native (sm_100a) implementation of Polyffusion's
+ * DDPM/DDIM sampling hot path.
+ *
+ * The reference (aik2mlj/polyffusion) is pure Python/PyTorch and has no FFI of its own; the
+ * boundary it exposes is the Python module API.  This header is the thin
+ * C ABI the Python drop-in classes in polyffusion_b200/ bind with ctypes.  Each entry point cites
+ * the reference interface it replaces (paths relative to /root/reference/polyffusion/).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
+ * code on failure (pf_last_error() gives the message); no C++ exceptions cross the ABI.  All
+ * tensor pointers are DEVICE pointers unless the name ends in _host.  The caller owns every tensor
+ * and the CUDA stream; the library owns packed weights and launch plans.  After the first call for
+ * a given (batch, n_cond, workspace) triple, pf_unet_forward performs no allocation and no
+ * host/device synchronisation, so a whole sampling step can be captured in a CUDA graph.
+ */
+#ifndef PF_B200_H
+#define PF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pf_unet pf_unet;
+typedef void* pf_stream; /* cudaStream_t */
+
+/* Geometry of stable_diffusion/model/unet.py:35-47 UNetModel.__init__ (keys of params/sdf_*.yaml). */
+typedef struct pf_unet_cfg {
+  int32_t in_channels;
+  int32_t out_channels;
+  int32_t channels;
+  int32_t n_res_blocks;
+  int32_t n_levels;                 /* len(channel_multipliers) */
+  int32_t channel_multipliers[8];
+  int32_t attention_levels[8];      /* 1 if level i has SpatialTransformers */
+  int32_t n_heads;
+  int32_t tf_layers;
+  int32_t d_cond;
+} pf_unet_cfg;
+
+const char* pf_last_error(void);
+const char* pf_version(void);
+
+/* UNetModel(**params)  -- stable_diffusion/model/unet.py:35 */
+int pf_unet_create(const pf_unet_cfg* cfg, pf_unet** out);
+void pf_unet_destroy(pf_unet* h);
+
+/* load_state_dict: one call per tensor, `name` is the reference state_dict key
+ * (e.g. "input_blocks.7.1.transformer_blocks.0.attn1.to_q.weight"); data is fp32, contiguous, on
+ * the device; it is read during pf_unet_finalize and not referenced afterwards.
+ * The special name "__time_freqs" carries the fp32 sinusoid frequency table
+ * (unet.py:160-164, `channels // 2` entries). */
+int pf_unet_set_weight(pf_unet* h, const char* name, const float* data, const int64_t* shape,
+                       int32_t ndim);
+/* Packs weights into split-bf16 tap-major GEMM operands, pre-combines biases, builds TMA maps. */
+int pf_unet_finalize(pf_unet* h, pf_stream stream);
+
+/* Bytes of scratch pf_unet_forward needs for this batch (images of height x width). */
+size_t pf_unet_workspace_bytes(pf_unet* h, int32_t batch, int32_t n_cond, int32_t height,
+                               int32_t width);
+
+/* UNetModel.forward(x, time_steps, cond) -- stable_diffusion/model/unet.py:171-196.
+ * x [B, in_channels, H, W] fp32 NCHW; time_steps [B] int64; cond [B, n_cond, d_cond] fp32;
+ * out [B, out_channels, H, W] fp32 NCHW. */
+int pf_unet_forward(pf_unet* h, const float* x, const int64_t* time_steps, const float* cond,
+                    int32_t batch, int32_t n_cond, int32_t height, int32_t width, float* out,
+                    void* workspace, size_t workspace_bytes, pf_stream stream);
+/* number of kernel launches one pf_unet_forward issues for the last-used plan */
+int32_t pf_unet_launch_count(pf_unet* h);
+
+/* Sampler step epilogues (elementwise over n = B*C*H*W floats).  Optional pointers may be NULL.
+ * e_uncond != NULL selects classifier-free guidance e = e_u + s*(e_c - e_u)
+ * (stable_diffusion/sampler/__init__.py:69-77); orig != NULL selects the RePaint blend
+ * x = (kn_a*orig + kn_b*noise_kn)*mask + x_prev*(1-mask) (sampler_sdf.py:322-336,
+ * sampler_ddim.py:355-359). */
+typedef struct pf_step_args {
+  const float* x;
+  const float* e_cond;
+  const float* e_uncond;
+  const float* noise;
+  const float* orig;
+  const float* mask;
+  const float* noise_kn;
+  float* x_prev;
+  float* x0;
+  float* e_t;
+  int64_t n;
+  int64_t noise_bcast; /* >0: noise holds this many elements and repeats over the batch */
+  float uncond_scale;
+  float c0, c1, c2, c3, c4; /* per-step coefficients, see below */
+  float temperature;
+  float kn_a, kn_b;
+} pf_step_args;
+
+/* SDFSampler.p_sample -- sampler_sdf.py:121-171.  c0 = sqrt_recip_alpha_bar[step],
+ * c1 = sqrt_recip_m1_alpha_bar[step], c2 = mean_x0_coef[step], c3 = mean_xt_coef[step],
+ * c4 = exp(0.5*log_var[step]). */
+int pf_sample_step_ddpm(const pf_step_args* a, pf_stream stream);
+/* DDIMSampler.get_x_prev_and_pred_x0 -- sampler_ddim.py:233-272.  c0 = ddim_sqrt_one_minus_alpha[i],
+ * c1 = ddim_alpha[i]**0.5, c2 = ddim_alpha_prev[i]**0.5, c3 = sqrt(1-alpha_prev-sigma^2),
+ * c4 = ddim_sigma[i]. */
+int pf_sample_step_ddim(const pf_step_args* a, pf_stream stream);
+/* DenoiseDiffusion.p_sample -- ddpm/__init__.py:66-88.  c0 = (1-alpha_t)/sqrt(1-alpha_bar_t),
+ * c1 = 1/sqrt(alpha_t), c2 = sqrt(sigma2_t). */
+int pf_sample_step_ddpm_legacy(const pf_step_args* a, pf_stream stream);
+/* q_sample: out = a*x0 + b*noise -- sampler_sdf.py:192, sampler_ddim.py:296-299 */
+int pf_q_sample(const float* x0, const float* noise, float* out, int64_t n, float a, float b,
+                pf_stream stream);
+
+/* Building-block ops (used by the parity tests; they allocate their own scratch and synchronise).
+ * conv: x NHWC fp32 [B,H,W,Cin] (Cin%64==0), w [Cout,Cin,k,k] (k in {1,3}), stride in {1,2},
+ * upsample in {0,1} (nearest 2x before the conv), bias/resid optional; out NHWC [B,Ho,Wo,Cout]. */
+int pf_op_conv2d_nhwc(const float* x, int32_t B, int32_t H, int32_t W, int32_t Cin, const float* w,
+                      int32_t Cout, int32_t ksize, int32_t stride, int32_t upsample,
+                      const float* bias, const float* resid, float* out, int32_t force_bn,
+                      pf_stream stream);
+/* softmax(q k^T / sqrt(d_head)) v per head: q [B,N,heads*64], k/v [B,Nk,heads*64] fp32 -> out
+ * [B,N,heads*64] fp32 (unet_attention.py:261-293 normal_attention, before to_out). */
+int pf_op_attention(const float* q, const float* k, const float* v, int32_t B, int32_t N,
+                    int32_t Nk, int32_t heads, float* out, pf_stream stream);
+/* GroupNorm(32 groups, eps) [+ SiLU] of an NHWC tensor -> fp32 NHWC (hi+lo of the operand). */
+int pf_op_groupnorm_nhwc(const float* x, int32_t B, int32_t HW, int32_t C, const float* gamma,
+                         const float* beta, float eps, int32_t silu, float* out, pf_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_B200_H */

@@ -1,0 +1,71 @@
+// Split-bf16 ("bf16x3") implicit-GEMM on tcgen05: parameter block shared by host and device.
+//
+//   D[m, n] = sum_seg sum_tap sum_c A_seg[pixel(m) shifted by tap, c] * W_seg[tap, n, c]
+//
+// A (activations) and W (weights) are each stored as two bf16 tensors (hi, lo) with
+// x ~= hi + lo; the kernel accumulates hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator,
+// which reproduces fp32 products to ~2^-16 relative ("bf16x3").
+//
+// A is a 4-D NHWC bf16 tensor {C, W, H, N} read by TMA boxes {64, box_w, box_h, 1}
+// (box_w*box_h = 128 output pixels); out-of-bounds coordinates are zero-filled by TMA, which
+// implements the conv padding.  W is a 2-D K-major tensor {K, rows}, read by boxes {64, BN}.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace pf {
+
+constexpr int GEMM_BM = 128;      // output rows (pixels / tokens) per CTA
+constexpr int GEMM_BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int GEMM_THREADS = 192; // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int GEMM_MAX_TAPS = 12;
+
+enum GemmOutMode : int {
+  OUT_F32 = 0,        // fp32 row-major [m, ldc] (+ addvec[img, n] + resid[m, n])
+  OUT_SPLIT = 1,      // bf16 hi/lo row-major [m, ldc]
+  OUT_SPLIT_T = 2,    // bf16 hi/lo transposed per image: [img][n][token]
+};
+
+struct alignas(64) GemmSeg {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  int ntaps;         // 1 (linear / 1x1) or 9 (3x3)
+  int kb_per_tap;    // channels / 64
+  int img_mul;       // TMA image coordinate = img * img_mul + tap_dq[tap]
+  int b_tap_stride;  // W row advance per tap (= total Cout of the packed weight)
+  int a_col0, b_row0, b_col0, pad0;
+  int a_img_zb, a_img_zh, a_col_zb, a_col_zh;  // per-batch (z) coordinate offsets
+  int b_row_zb, b_row_zh, b_col_zb, b_col_zh;
+  signed char tap_dx[GEMM_MAX_TAPS], tap_dy[GEMM_MAX_TAPS], tap_dq[GEMM_MAX_TAPS];
+  int pad1[3];
+};
+
+struct alignas(64) GemmParams {
+  GemmSeg seg[2];
+  int nseg;
+  int nstages;
+  int tiles_per_img;  // M tiles per image
+  int tiles_x;        // tiles along W inside an image
+  int box_w, box_h;
+  int zdiv;           // batch index z -> (zb = z / zdiv, zh = z % zdiv)
+  int mode;
+  int n_tiles, m_tiles, z_count;  // tile grid: n fastest, then m, then z
+  float* out;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  long long ldc, out_zb, out_zh, out_img;
+  const float* addvec;  // [img, addvec_ld] or null
+  const float* resid;   // [m, ldr] or null
+  long long addvec_ld, ldr;
+};
+
+// smem bytes for a given BN / stage count (incl. 1 KB alignment slack)
+inline int gemm_stage_bytes(int bn) { return 2 * GEMM_BM * 128 + 2 * bn * 128; }
+inline int gemm_smem_bytes(int bn, int nstages) { return nstages * gemm_stage_bytes(bn) + 1024; }
+
+// persistent launch: min(#tiles, num_ctas) CTAs
+cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t stream);
+cudaError_t gemm_init_attrs();
+
+}  // namespace pf

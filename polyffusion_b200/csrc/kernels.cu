@@ -1,0 +1,655 @@
+// Non-GEMM kernels of the UNet hot path.  See kernels.cuh for the contract of each launcher.
+// All fp32 arithmetic here avoids fast-math so results track the reference's ATen fp32 ops.
+#include "common.cuh"
+#include "kernels.cuh"
+#include <math.h>
+
+namespace pf {
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+
+// ------------------------------------------------------------------------------------------------
+// conv_in: NCHW fp32 (tiny Cin) -> NHWC fp32, 3x3 pad 1.
+// block = 256 threads = 64 pixels of one row x 4 channel quarters.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x,
+                                                      const float* __restrict__ w,
+                                                      const float* __restrict__ bias,
+                                                      float* __restrict__ out, int Cin, int H, int W,
+                                                      int Cout) {
+  extern __shared__ float sm[];
+  const int K = Cin * 9;
+  float* sw = sm;                    // [K][Cout]
+  float* sx = sm + K * Cout;         // [Cin][3][66]
+  const int b = blockIdx.z, y = blockIdx.y, xb = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < K * Cout; i += 256) {
+    const int co = i / K, k = i % K;  // w is [Cout][Cin][3][3] -> k = ci*9 + ky*3 + kx
+    sw[k * Cout + co] = w[i];
+  }
+  for (int i = threadIdx.x; i < Cin * 3 * 66; i += 256) {
+    const int ci = i / (3 * 66), r = (i / 66) % 3, xx = i % 66;
+    const int gy = y + r - 1, gx = xb + xx - 1;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = x[((static_cast<long long>(b) * Cin + ci) * H + gy) * W + gx];
+    sx[i] = v;
+  }
+  __syncthreads();
+  const int p = threadIdx.x >> 2, q = threadIdx.x & 3;
+  const int cpq = Cout / 4;  // channels per quarter (16 for Cout = 64)
+  if (xb + p >= W) return;
+  float* o = out + ((static_cast<long long>(b) * H + y) * W + xb + p) * Cout + q * cpq;
+  for (int c0 = 0; c0 < cpq; c0 += 4) {
+    float4 acc = *reinterpret_cast<const float4*>(bias + q * cpq + c0);
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int r = 0; r < 3; ++r)
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = sx[(ci * 3 + r) * 66 + p + kx];
+          const float4 ww = *reinterpret_cast<const float4*>(sw + (ci * 9 + r * 3 + kx) * Cout + q * cpq + c0);
+          acc.x = fmaf(v, ww.x, acc.x);
+          acc.y = fmaf(v, ww.y, acc.y);
+          acc.z = fmaf(v, ww.z, acc.z);
+          acc.w = fmaf(v, ww.w, acc.w);
+        }
+    *reinterpret_cast<float4*>(o + c0) = acc;
+  }
+}
+
+void launch_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int Cin,
+                    int H, int W, int Cout, cudaStream_t s) {
+  dim3 grid((W + 63) / 64, H, B);
+  const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + Cin * 3 * 66) * sizeof(float);
+  conv_in_kernel<<<grid, 256, smem, s>>>(x, w, bias, out, Cin, H, W, Cout);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ src,
+                                                       double* __restrict__ acc, int HW, int Cs,
+                                                       int Ctot, int coff, int pix_per_block) {
+  __shared__ float s_sum[256 * 4];
+  __shared__ float s_sq[256 * 4];
+  const int b = blockIdx.y;
+  const int nvec = Cs >> 2;            // float4 per pixel
+  const int rows = 256 / nvec;         // pixel rows processed in parallel
+  const int v = threadIdx.x % nvec, pr = threadIdx.x / nvec;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), sq = sum;
+  const float4* base = reinterpret_cast<const float4*>(src + static_cast<long long>(b) * HW * Cs);
+  if (pr < rows) {
+    for (int p = p0 + pr; p < p1; p += rows) {
+      const float4 a = __ldg(base + static_cast<long long>(p) * nvec + v);
+      sum.x += a.x; sum.y += a.y; sum.z += a.z; sum.w += a.w;
+      sq.x = fmaf(a.x, a.x, sq.x); sq.y = fmaf(a.y, a.y, sq.y);
+      sq.z = fmaf(a.z, a.z, sq.z); sq.w = fmaf(a.w, a.w, sq.w);
+    }
+  }
+  reinterpret_cast<float4*>(s_sum)[threadIdx.x] = sum;
+  reinterpret_cast<float4*>(s_sq)[threadIdx.x] = sq;
+  __syncthreads();
+  if (threadIdx.x < Cs) {
+    const int c = threadIdx.x;
+    double ts = 0.0, tq = 0.0;
+    for (int r = 0; r < rows; ++r) {
+      ts += static_cast<double>(s_sum[(r * nvec) * 4 + c]);
+      tq += static_cast<double>(s_sq[(r * nvec) * 4 + c]);
+    }
+    double* a = acc + (static_cast<long long>(b) * Ctot + coff + c) * 2;
+    atomicAdd(a, ts);
+    atomicAdd(a + 1, tq);
+  }
+}
+
+void launch_gn_stats(const float* src, double* acc, int B, int HW, int Cs, int Ctot, int coff,
+                     cudaStream_t s) {
+  // aim for >= ~4 waves of blocks; each block reduces pix_per_block pixels
+  int chunks = max(1, min(HW / 64, (148 * 8 + B - 1) / B));
+  int ppb = (HW + chunks - 1) / chunks;
+  chunks = (HW + ppb - 1) / ppb;
+  dim3 grid(chunks, B);
+  gn_stats_kernel<<<grid, 256, 0, s>>>(src, acc, HW, Cs, Ctot, coff, ppb);
+}
+
+__global__ void gn_finalize_kernel(const double* __restrict__ acc, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ scale,
+                                   float* __restrict__ shift, int HW, int Ctot, int groups,
+                                   float eps) {
+  const int b = blockIdx.x;
+  const int cpg = Ctot / groups;
+  for (int c = threadIdx.x; c < Ctot; c += blockDim.x) {
+    const int g = c / cpg;
+    double ts = 0.0, tq = 0.0;
+    const double* a = acc + (static_cast<long long>(b) * Ctot + g * cpg) * 2;
+    for (int i = 0; i < cpg; ++i) {
+      ts += a[2 * i];
+      tq += a[2 * i + 1];
+    }
+    const double n = static_cast<double>(HW) * cpg;
+    const double mean = ts / n;
+    double var = tq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * rstd;
+    scale[static_cast<long long>(b) * Ctot + c] = sc;
+    shift[static_cast<long long>(b) * Ctot + c] = beta[c] - static_cast<float>(mean) * sc;
+  }
+}
+
+void launch_gn_finalize(const double* acc, const float* gamma, const float* beta, float* scale,
+                        float* shift, int B, int HW, int Ctot, int groups, float eps, cudaStream_t s) {
+  gn_finalize_kernel<<<B, 256, 0, s>>>(acc, gamma, beta, scale, shift, HW, Ctot, groups, eps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// act_split: fp32 NHWC (one or two concatenated sources) -> split bf16 operand tensor
+// one thread = 8 channels of one pixel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) act_split_kernel(
+    const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
+    const float* __restrict__ scale, const float* __restrict__ shift, int silu, int layout,
+    bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int H, int W) {
+  const int C = C0 + C1;
+  const int c8n = C >> 3;
+  const long long total = static_cast<long long>(B) * H * W * c8n;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % c8n) * 8;
+  const long long pix = idx / c8n;  // b*H*W + y*W + x
+  const int b = static_cast<int>(pix / (static_cast<long long>(H) * W));
+  float v[8];
+  {
+    const float* sp = (c < C0) ? src0 + pix * C0 + c : src1 + pix * C1 + (c - C0);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(sp));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+    v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+  }
+  if (scale) {
+    const float* sc = scale + static_cast<long long>(b) * C + c;
+    const float* sh = shift + static_cast<long long>(b) * C + c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], __ldg(sc + i), __ldg(sh + i));
+  }
+  if (silu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+  }
+  uint4 h, l;
+  split2(v[0], v[1], h.x, l.x);
+  split2(v[2], v[3], h.y, l.y);
+  split2(v[4], v[5], h.z, l.z);
+  split2(v[6], v[7], h.w, l.w);
+  if (layout == XF_SAME) {
+    *reinterpret_cast<uint4*>(out_hi + pix * C + c) = h;
+    *reinterpret_cast<uint4*>(out_lo + pix * C + c) = l;
+  } else {
+    const int rem = static_cast<int>(pix % (static_cast<long long>(H) * W));
+    const int y = rem / W, x = rem % W;
+    if (layout == XF_UP2) {
+      const int H2 = 2 * H, W2 = 2 * W;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const long long o = ((static_cast<long long>(b) * H2 + 2 * y + dy) * W2 + 2 * x + dx) * C + c;
+          *reinterpret_cast<uint4*>(out_hi + o) = h;
+          *reinterpret_cast<uint4*>(out_lo + o) = l;
+        }
+    } else {  // XF_S2D: [b*4 + (y&1)*2 + (x&1)][H/2][W/2][C]
+      const int Hh = H >> 1, Wh = W >> 1;
+      const long long o =
+          (((static_cast<long long>(b) * 4 + (y & 1) * 2 + (x & 1)) * Hh + (y >> 1)) * Wh + (x >> 1)) * C + c;
+      *reinterpret_cast<uint4*>(out_hi + o) = h;
+      *reinterpret_cast<uint4*>(out_lo + o) = l;
+    }
+  }
+}
+
+void launch_act_split(const float* src0, int C0, const float* src1, int C1, const float* scale,
+                      const float* shift, int silu, int layout, bf16* out_hi, bf16* out_lo, int B,
+                      int H, int W, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * H * W * ((C0 + C1) >> 3);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  act_split_kernel<<<blocks, 256, 0, s>>>(src0, C0, src1, C1, scale, shift, silu, layout, out_hi,
+                                          out_lo, B, H, W);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm + split (warp per row, values held in registers)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__ src,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps,
+                                                       bf16* __restrict__ out_hi,
+                                                       bf16* __restrict__ out_lo, long long rows,
+                                                       int C) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nch = C >> 7;  // float4 chunks per lane (C / 128), <= 4
+  float4 v[4];
+  const float4* sp = reinterpret_cast<const float4*>(src + row * C);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < nch) {
+      v[i] = __ldg(sp + i * 32 + lane);
+      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  const float mean = warp_sum(sum) / static_cast<float>(C);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < nch) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += a * a + b * b + c * c + d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < nch) {
+      const int c0 = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c0));
+      const float o0 = (v[i].x - mean) * rstd * g.x + bb.x;
+      const float o1 = (v[i].y - mean) * rstd * g.y + bb.y;
+      const float o2 = (v[i].z - mean) * rstd * g.z + bb.z;
+      const float o3 = (v[i].w - mean) * rstd * g.w + bb.w;
+      uint2 h, l;
+      split2(o0, o1, h.x, l.x);
+      split2(o2, o3, h.y, l.y);
+      *reinterpret_cast<uint2*>(out_hi + row * C + c0) = h;
+      *reinterpret_cast<uint2*>(out_lo + row * C + c0) = l;
+    }
+}
+
+void launch_ln_split(const float* src, const float* gamma, const float* beta, float eps,
+                     bf16* out_hi, bf16* out_lo, long long rows, int C, cudaStream_t s) {
+  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  ln_split_kernel<<<blocks, 256, 0, s>>>(src, gamma, beta, eps, out_hi, out_lo, rows, C);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GeGLU + split: one thread = 8 outputs
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float g) {
+  return 0.5f * g * (1.0f + erff(g * 0.70710678118654752440f));
+}
+
+__global__ void __launch_bounds__(256) geglu_split_kernel(const float* __restrict__ src,
+                                                          bf16* __restrict__ out_hi,
+                                                          bf16* __restrict__ out_lo, long long rows,
+                                                          int F) {
+  const int f8n = F >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= rows * f8n) return;
+  const long long row = idx / f8n;
+  const int f = static_cast<int>(idx % f8n) * 8;
+  const float* xp = src + row * 2 * F + f;
+  const float* gp = xp + F;
+  float xv[8], gv[8];
+  *reinterpret_cast<float4*>(xv) = __ldg(reinterpret_cast<const float4*>(xp));
+  *reinterpret_cast<float4*>(xv + 4) = __ldg(reinterpret_cast<const float4*>(xp) + 1);
+  *reinterpret_cast<float4*>(gv) = __ldg(reinterpret_cast<const float4*>(gp));
+  *reinterpret_cast<float4*>(gv + 4) = __ldg(reinterpret_cast<const float4*>(gp) + 1);
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = xv[i] * gelu_erf(gv[i]);
+  uint4 h, l;
+  split2(o[0], o[1], h.x, l.x);
+  split2(o[2], o[3], h.y, l.y);
+  split2(o[4], o[5], h.z, l.z);
+  split2(o[6], o[7], h.w, l.w);
+  *reinterpret_cast<uint4*>(out_hi + row * F + f) = h;
+  *reinterpret_cast<uint4*>(out_lo + row * F + f) = l;
+}
+
+void launch_geglu_split(const float* src, bf16* out_hi, bf16* out_lo, long long rows, int F,
+                        cudaStream_t s) {
+  const long long total = rows * (F >> 3);
+  geglu_split_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(src, out_hi, out_lo,
+                                                                                  rows, F);
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax + split: warp per row, Nk <= 1024 (8 float4 per lane)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_split_kernel(const float* __restrict__ S, float scale,
+                                                            bf16* __restrict__ out_hi,
+                                                            bf16* __restrict__ out_lo,
+                                                            long long rows, int Nk) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nch = Nk >> 7;
+  float4 v[8];
+  const float4* sp = reinterpret_cast<const float4*>(S + row * Nk);
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nch) {
+      float4 a = __ldg(sp + i * 32 + lane);
+      a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+      v[i] = a;
+      mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+    }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nch) {
+      v[i].x = expf(v[i].x - mx); v[i].y = expf(v[i].y - mx);
+      v[i].z = expf(v[i].z - mx); v[i].w = expf(v[i].w - mx);
+      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nch) {
+      const int c0 = (i * 32 + lane) * 4;
+      uint2 h, l;
+      split2(v[i].x * inv, v[i].y * inv, h.x, l.x);
+      split2(v[i].z * inv, v[i].w * inv, h.y, l.y);
+      *reinterpret_cast<uint2*>(out_hi + row * Nk + c0) = h;
+      *reinterpret_cast<uint2*>(out_lo + row * Nk + c0) = l;
+    }
+}
+
+void launch_softmax_split(const float* S, float scale, bf16* out_hi, bf16* out_lo, long long rows,
+                          int Nk, cudaStream_t s) {
+  softmax_split_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(S, scale, out_hi,
+                                                                               out_lo, rows, Nk);
+}
+
+// ------------------------------------------------------------------------------------------------
+// timestep embedding + small linears
+// ------------------------------------------------------------------------------------------------
+__global__ void time_sinusoid_kernel(const long long* __restrict__ t,
+                                     const float* __restrict__ freqs, float* __restrict__ out, int B,
+                                     int half) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, j = i % half;
+  // args = t.float() * f_j ; emb = cat([cos(args), sin(args)])  (unet.py:165-169).  The frequency
+  // table f_j = exp(-ln(10000) * j / half) is evaluated by the host exactly as the reference does.
+  const float a = __fmul_rn(static_cast<float>(t[b]), freqs[j]);
+  out[static_cast<long long>(b) * 2 * half + j] = cosf(a);
+  out[static_cast<long long>(b) * 2 * half + half + j] = sinf(a);
+}
+void launch_time_sinusoid(const long long* t, const float* freqs, float* out, int B, int half,
+                          cudaStream_t s) {
+  time_sinusoid_kernel<<<(B * half + 127) / 128, 128, 0, s>>>(t, freqs, out, B, half);
+}
+
+// test helpers: fp32 = hi + lo, and [rows, C] -> transposed split [C, rows] per image
+__global__ void merge_split_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo,
+                                   float* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+void launch_merge_split(const bf16* hi, const bf16* lo, float* out, long long n, cudaStream_t s) {
+  merge_split_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(hi, lo, out, n);
+}
+__global__ void transpose_split_kernel(const float* __restrict__ src, bf16* __restrict__ hi,
+                                       bf16* __restrict__ lo, int rows, int C) {
+  // src [img][rows][C] -> out [img][C][rows]
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  const long long per = static_cast<long long>(rows) * C;
+  const long long img = blockIdx.y;
+  if (i >= per) return;
+  const int r = static_cast<int>(i % rows), c = static_cast<int>(i / rows);
+  bf16 h, l;
+  split_bf16(src[img * per + static_cast<long long>(r) * C + c], h, l);
+  hi[img * per + i] = h;
+  lo[img * per + i] = l;
+}
+void launch_transpose_split(const float* src, bf16* hi, bf16* lo, int imgs, int rows, int C,
+                            cudaStream_t s) {
+  const long long per = static_cast<long long>(rows) * C;
+  dim3 grid(static_cast<unsigned>((per + 255) / 256), imgs);
+  transpose_split_kernel<<<grid, 256, 0, s>>>(src, hi, lo, rows, C);
+}
+
+// warp per output element
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in,
+                                                           long long ld_in,
+                                                           const float* __restrict__ W,
+                                                           const float* __restrict__ bias,
+                                                           float* __restrict__ out, long long ld_out,
+                                                           int B, int N, int K, int in_act) {
+  const long long o = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (o >= static_cast<long long>(B) * N) return;
+  const int lane = threadIdx.x & 31;
+  const int b = static_cast<int>(o / N), n = static_cast<int>(o % N);
+  const float* ip = in + b * ld_in;
+  const float* wp = W + static_cast<long long>(n) * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float v = __ldg(ip + k);
+    if (in_act) v = silu_f(v);
+    acc = fmaf(v, __ldg(wp + k), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[b * ld_out + n] = acc + (bias ? bias[n] : 0.f);
+}
+void launch_small_linear(const float* in, long long ld_in, const float* W, const float* bias,
+                         float* out, long long ld_out, int B, int N, int K, int in_act,
+                         cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * N;
+  small_linear_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, s>>>(in, ld_in, W, bias, out,
+                                                                              ld_out, B, N, K, in_act);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_out: GN-apply + SiLU + conv3x3 (C -> Cout<=4) -> NCHW.  16x16 pixel tile + halo in smem.
+// ------------------------------------------------------------------------------------------------
+constexpr int CO_T = 16;
+__global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__ h,
+                                                       const float* __restrict__ scale,
+                                                       const float* __restrict__ shift,
+                                                       const float* __restrict__ w,
+                                                       const float* __restrict__ bias,
+                                                       float* __restrict__ out, int H, int W, int C,
+                                                       int Cout) {
+  extern __shared__ float sm[];
+  const int pitch = C + 4;
+  float* st = sm;                                        // [(T+2)*(T+2)][pitch]
+  float* sw = sm + (CO_T + 2) * (CO_T + 2) * pitch;      // [Cout][9][C]
+  const int b = blockIdx.z, ty = blockIdx.y * CO_T, tx = blockIdx.x * CO_T;
+  const int c4n = C >> 2;
+  for (int i = threadIdx.x; i < Cout * 9 * C; i += 256) {
+    // w [Cout][C][3][3] -> sw[co][tap][c]
+    const int co = i / (9 * C), r = i % (9 * C);
+    const int tap = r / C, c = r % C;
+    sw[i] = w[(static_cast<long long>(co) * C + c) * 9 + tap];
+  }
+  const float* sc = scale + static_cast<long long>(b) * C;
+  const float* sh = shift + static_cast<long long>(b) * C;
+  for (int i = threadIdx.x; i < (CO_T + 2) * (CO_T + 2) * c4n; i += 256) {
+    const int pix = i / c4n, c = (i % c4n) * 4;
+    const int gy = ty + pix / (CO_T + 2) - 1, gx = tx + pix % (CO_T + 2) - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(
+          h + ((static_cast<long long>(b) * H + gy) * W + gx) * C + c));
+      v.x = silu_f(fmaf(a.x, sc[c + 0], sh[c + 0]));
+      v.y = silu_f(fmaf(a.y, sc[c + 1], sh[c + 1]));
+      v.z = silu_f(fmaf(a.z, sc[c + 2], sh[c + 2]));
+      v.w = silu_f(fmaf(a.w, sc[c + 3], sh[c + 3]));
+    }
+    *reinterpret_cast<float4*>(st + pix * pitch + c) = v;
+  }
+  __syncthreads();
+  const int py = threadIdx.x / CO_T, px = threadIdx.x % CO_T;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tap = 0; tap < 9; ++tap) {
+    const float* ip = st + ((py + tap / 3) * (CO_T + 2) + px + tap % 3) * pitch;
+    for (int c = 0; c < C; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(ip + c);
+#pragma unroll
+      for (int co = 0; co < 4; ++co)
+        if (co < Cout) {
+          const float4 ww = *reinterpret_cast<const float4*>(sw + (co * 9 + tap) * C + c);
+          acc[co] = fmaf(v.x, ww.x, acc[co]);
+          acc[co] = fmaf(v.y, ww.y, acc[co]);
+          acc[co] = fmaf(v.z, ww.z, acc[co]);
+          acc[co] = fmaf(v.w, ww.w, acc[co]);
+        }
+    }
+  }
+  const int gy = ty + py, gx = tx + px;
+  if (gy < H && gx < W)
+    for (int co = 0; co < Cout; ++co)
+      out[((static_cast<long long>(b) * Cout + co) * H + gy) * W + gx] = acc[co] + bias[co];
+}
+
+void launch_conv_out(const float* h, const float* scale, const float* shift, const float* w,
+                     const float* bias, float* out, int B, int H, int W, int C, int Cout,
+                     cudaStream_t s) {
+  static bool attr_set = false;
+  const size_t smem =
+      (static_cast<size_t>(CO_T + 2) * (CO_T + 2) * (C + 4) + static_cast<size_t>(Cout) * 9 * C) * sizeof(float);
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  dim3 grid((W + CO_T - 1) / CO_T, (H + CO_T - 1) / CO_T, B);
+  conv_out_kernel<<<grid, 256, smem, s>>>(h, scale, shift, w, bias, out, H, W, C, Cout);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing / misc
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out_hi,
+                                   bf16* __restrict__ out_lo, int Cout, int Cin, int taps,
+                                   int cout_total, int row0) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  if (i >= total) return;
+  // destination-ordered index: (tap, co, ci)
+  const int ci = static_cast<int>(i % Cin);
+  const int co = static_cast<int>((i / Cin) % Cout);
+  const int tap = static_cast<int>(i / (static_cast<long long>(Cin) * Cout));
+  const float v = w[(static_cast<long long>(co) * Cin + ci) * taps + tap];
+  bf16 h, l;
+  split_bf16(v, h, l);
+  const long long o = (static_cast<long long>(tap) * cout_total + row0 + co) * Cin + ci;
+  out_hi[o] = h;
+  out_lo[o] = l;
+}
+void launch_pack_weight(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin, int taps,
+                        int cout_total, int row0, cudaStream_t s) {
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  pack_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+      w, out_hi, out_lo, Cout, Cin, taps, cout_total, row0);
+}
+
+__global__ void vec_add_kernel(const float* a, const float* b, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+void launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t s) {
+  vec_add_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, out, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampler step epilogues.  Every fp32 op is individually rounded (__fmul_rn/__fadd_rn, no FMA
+// contraction) in the order the reference's ATen elementwise ops run, so that given identical
+// inputs the result is the same fp32 value the reference computes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float guided_eps(const StepArgs& a, long long i) {
+  const float ec = a.e_cond[i];
+  if (!a.e_uncond) return ec;
+  const float eu = a.e_uncond[i];
+  // e_u + s * (e_c - e_u)   (sampler/__init__.py:77)
+  return __fadd_rn(eu, __fmul_rn(a.uncond_scale, __fsub_rn(ec, eu)));
+}
+__device__ __forceinline__ float step_noise(const StepArgs& a, long long i) {
+  if (!a.noise) return 0.f;
+  const float nz = a.noise_bcast > 0 ? a.noise[i % a.noise_bcast] : a.noise[i];
+  return __fmul_rn(nz, a.temperature);
+}
+__device__ __forceinline__ float repaint_blend(const StepArgs& a, long long i, float x_unkn) {
+  if (!a.orig) return x_unkn;
+  // x_kn = kn_a*orig + kn_b*noise ; x = x_kn*mask + x_unkn*(1-mask)  (sampler_sdf.py:192,336)
+  const float nk = a.noise_kn ? a.noise_kn[i] : 0.f;
+  const float xk = __fadd_rn(__fmul_rn(a.kn_a, a.orig[i]), __fmul_rn(a.kn_b, nk));
+  const float m = a.mask[i];
+  return __fadd_rn(__fmul_rn(xk, m), __fmul_rn(x_unkn, __fsub_rn(1.0f, m)));
+}
+
+__global__ void __launch_bounds__(256) step_ddpm_kernel(const StepArgs a) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= a.n) return;
+  const float x = a.x[i];
+  const float e = guided_eps(a, i);
+  // c0 = sqrt_recip_alpha_bar, c1 = sqrt_recip_m1_alpha_bar, c2 = mean_x0_coef, c3 = mean_xt_coef,
+  // c4 = exp(0.5*log_var)
+  const float x0 = __fsub_rn(__fmul_rn(a.c0, x), __fmul_rn(a.c1, e));
+  const float mean = __fadd_rn(__fmul_rn(a.c2, x0), __fmul_rn(a.c3, x));
+  const float xp = __fadd_rn(mean, __fmul_rn(a.c4, step_noise(a, i)));
+  a.x_prev[i] = repaint_blend(a, i, xp);
+  if (a.x0) a.x0[i] = x0;
+  if (a.e_t) a.e_t[i] = e;
+}
+void launch_step_ddpm(const StepArgs& a, cudaStream_t s) {
+  step_ddpm_kernel<<<static_cast<unsigned>((a.n + 255) / 256), 256, 0, s>>>(a);
+}
+
+__global__ void __launch_bounds__(256) step_ddim_kernel(const StepArgs a) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= a.n) return;
+  const float x = a.x[i];
+  const float e = guided_eps(a, i);
+  // c0 = sqrt(1-alpha), c1 = alpha**0.5, c2 = alpha_prev**0.5, c3 = sqrt(1-alpha_prev-sigma^2),
+  // c4 = sigma
+  const float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(a.c0, e)), a.c1);
+  const float dir = __fmul_rn(a.c3, e);
+  float xp = __fadd_rn(__fmul_rn(a.c2, x0), dir);
+  xp = __fadd_rn(xp, __fmul_rn(a.c4, step_noise(a, i)));
+  a.x_prev[i] = repaint_blend(a, i, xp);
+  if (a.x0) a.x0[i] = x0;
+  if (a.e_t) a.e_t[i] = e;
+}
+void launch_step_ddim(const StepArgs& a, cudaStream_t s) {
+  step_ddim_kernel<<<static_cast<unsigned>((a.n + 255) / 256), 256, 0, s>>>(a);
+}
+
+__global__ void __launch_bounds__(256) step_ddpm_legacy_kernel(const StepArgs a) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= a.n) return;
+  // c0 = (1-alpha)/sqrt(1-alpha_bar), c1 = 1/sqrt(alpha), c2 = sqrt(sigma2)  (ddpm/__init__.py:79-88)
+  const float mean = __fmul_rn(a.c1, __fsub_rn(a.x[i], __fmul_rn(a.c0, a.e_cond[i])));
+  a.x_prev[i] = __fadd_rn(mean, __fmul_rn(a.c2, a.noise ? a.noise[i] : 0.f));
+}
+void launch_step_ddpm_legacy(const StepArgs& a, cudaStream_t s) {
+  step_ddpm_legacy_kernel<<<static_cast<unsigned>((a.n + 255) / 256), 256, 0, s>>>(a);
+}
+
+__global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__ x0,
+                                                       const float* __restrict__ noise,
+                                                       float* __restrict__ out, long long n, float a,
+                                                       float b) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  out[i] = __fadd_rn(__fmul_rn(a, x0[i]), __fmul_rn(b, noise[i]));
+}
+void launch_q_sample(const float* x0, const float* noise, float* out, long long n, float a, float b,
+                     cudaStream_t s) {
+  q_sample_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x0, noise, out, n, a, b);
+}
+
+}  // namespace pf

@@ -1,0 +1,98 @@
+// Non-GEMM kernels of the UNet hot path (all HBM-bound or tiny): GroupNorm statistics, the
+// "operand transform" passes that turn fp32 NHWC activations into split-bf16 GEMM operands
+// (fusing GN-apply / SiLU / LayerNorm / GeGLU / softmax / concat / 2x-upsample / stride-2
+// re-layout), the fp32 edge convolutions (Cin=2 in, Cout=2 out), small per-sample linears, and the
+// sampler step epilogues.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace pf {
+
+typedef __nv_bfloat16 bf16;
+
+// x NCHW [B,Cin,H,W] -> out NHWC [B,H,W,Cout], 3x3 pad 1, fp32 (unet.py:79 first conv)
+void launch_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int Cin,
+                    int H, int W, int Cout, cudaStream_t s);
+
+// per-(sample, channel) sum / sum-of-squares (fp64 atomics) of an NHWC tensor [B,HW,Cs] written at
+// channel offset coff of acc [B, Ctot, 2]
+void launch_gn_stats(const float* src, double* acc, int B, int HW, int Cs, int Ctot, int coff,
+                     cudaStream_t s);
+// acc -> scale/shift [B, Ctot] for GroupNorm(groups, eps) with affine gamma/beta
+void launch_gn_finalize(const double* acc, const float* gamma, const float* beta, float* scale,
+                        float* shift, int B, int HW, int Ctot, int groups, float eps, cudaStream_t s);
+
+enum XformLayout : int { XF_SAME = 0, XF_UP2 = 1, XF_S2D = 2 };
+// out_hi/lo[b, y', x', c] = split(act(scale*cat(src0,src1) + shift)); act = SiLU if silu.
+void launch_act_split(const float* src0, int C0, const float* src1, int C1, const float* scale,
+                      const float* shift, int silu, int layout, bf16* out_hi, bf16* out_lo, int B,
+                      int H, int W, cudaStream_t s);
+
+// LayerNorm over C (eps) + affine -> split bf16 [rows, C]; C multiple of 128, <= 512
+void launch_ln_split(const float* src, const float* gamma, const float* beta, float eps,
+                     bf16* out_hi, bf16* out_lo, long long rows, int C, cudaStream_t s);
+// GeGLU: in [rows, 2F] -> split(in[:, :F] * gelu_erf(in[:, F:])) [rows, F]
+void launch_geglu_split(const float* src, bf16* out_hi, bf16* out_lo, long long rows, int F,
+                        cudaStream_t s);
+// softmax(scale * S) over last dim Nk (multiple of 128, <= 1024) -> split bf16
+void launch_softmax_split(const float* S, float scale, bf16* out_hi, bf16* out_lo, long long rows,
+                          int Nk, cudaStream_t s);
+
+// sinusoidal timestep embedding [B, 2*half] = [cos(t f_i), sin(t f_i)] (unet.py:151-169)
+void launch_time_sinusoid(const long long* t, const float* freqs, float* out, int B, int half,
+                          cudaStream_t s);
+// test helpers
+void launch_merge_split(const bf16* hi, const bf16* lo, float* out, long long n, cudaStream_t s);
+void launch_transpose_split(const float* src, bf16* hi, bf16* lo, int imgs, int rows, int C,
+                            cudaStream_t s);
+// out[b, n] = W[n,:] . act(in[b,:]) + bias[n]; in_act: 0 none, 1 SiLU.  fp32 exact-order-free.
+void launch_small_linear(const float* in, long long ld_in, const float* W, const float* bias,
+                         float* out, long long ld_out, int B, int N, int K, int in_act,
+                         cudaStream_t s);
+
+// GroupNorm-apply + SiLU + conv3x3 (C -> Cout small) -> NCHW out (unet.py:145-149)
+void launch_conv_out(const float* h, const float* scale, const float* shift, const float* w,
+                     const float* bias, float* out, int B, int H, int W, int C, int Cout,
+                     cudaStream_t s);
+
+// weight packing: w [Cout, Cin, kh, kw] fp32 -> split bf16 [kh*kw][Cout_total][Cin] rows at row0
+void launch_pack_weight(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin, int taps,
+                        int cout_total, int row0, cudaStream_t s);
+// out[i] = a[i] + b[i] (bias pre-combination); b may be null
+void launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t s);
+
+// ------------------------------------------------------------------ sampler step epilogues
+struct StepArgs {
+  // all tensors [n] fp32 contiguous (NCHW flattened); optional ones may be null
+  const float* x;        // x_t
+  const float* e_cond;   // eps (conditional half, or the only eps)
+  const float* e_uncond; // eps for the unconditional half (CFG), or null
+  const float* noise;    // N(0,1) for the reverse step, or null (=> 0)
+  const float* orig;     // RePaint known image, or null
+  const float* mask;     // RePaint mask
+  const float* noise_kn; // noise used to diffuse `orig`
+  float* x_prev;         // output
+  float* x0;             // optional output
+  float* e_t;            // optional output (guided eps)
+  long long n;
+  long long noise_bcast; // if >0: noise has this many elements, broadcast over batch (repeat_noise)
+  float uncond_scale;
+  // DDPM (sampler_sdf.py:121-171): x0 = c_rab*x - c_rm1*e; mean = c_x0*x0 + c_xt*x;
+  //   x_prev = mean + exp(0.5*log_var)*noise*temperature
+  // DDIM (sampler_ddim.py:233-272): x0 = (x - c_s1m*e)/sqrt(alpha); x_prev = sqrt(alpha_prev)*x0
+  //   + sqrt(1-alpha_prev-sigma^2)*e + sigma*noise*temperature
+  float c0, c1, c2, c3, c4;
+  float temperature;
+  float kn_a, kn_b;      // q_sample(orig): kn_a*orig + kn_b*noise_kn
+};
+void launch_step_ddpm(const StepArgs& a, cudaStream_t s);
+void launch_step_ddim(const StepArgs& a, cudaStream_t s);
+// legacy DDPM (ddpm/__init__.py:66-88): mean = (x - c0*e)*c1 ; x_prev = mean + c2*noise
+void launch_step_ddpm_legacy(const StepArgs& a, cudaStream_t s);
+// out = a*x0 + b*noise
+void launch_q_sample(const float* x0, const float* noise, float* out, long long n, float a, float b,
+                     cudaStream_t s);
+
+}  // namespace pf

@@ -1,0 +1,1358 @@
+// UNet forward plan + C ABI (include/pf_b200.h).
+//
+// pf_unet_forward mirrors stable_diffusion/model/unet.py:171-196 (UNetModel.forward) of the
+// reference, restructured for B200:
+//   * activations live in HBM as fp32 NHWC; every GEMM-shaped op (conv3x3 / conv1x1 / linear /
+//     QK^T / PV) runs on the tcgen05 split-bf16 implicit-GEMM kernel (gemm_tc.cu);
+//   * GroupNorm+SiLU, LayerNorm, GeGLU, softmax, channel concat (th.cat, unet.py:192), nearest-2x
+//     upsample (unet.py:236) and the stride-2 re-layout (unet.py:252) are folded into the single
+//     HBM pass that produces the next GEMM's split-bf16 operand;
+//   * bias, time-embedding add (unet.py:312-316), residual adds and the ResBlock 1x1 skip conv
+//     (second K-segment accumulating into the same TMEM tile) are folded into the GEMM;
+//   * cross-attention with n_cond == 1 (softmax over one key == 1) collapses to a per-sample
+//     vector to_out(to_v(cond)) added in the self-attention out-projection epilogue.
+// The first call for a (batch, n_cond, H, W, workspace) builds a static launch plan (a flat op list
+// with pre-encoded TMA maps); later calls only replay launches: no allocation, no host sync.
+#include <memory>
+#include <unordered_map>
+
+#include "../../include/pf_b200.h"
+#include "host_util.h"
+
+namespace pf {
+
+// =================================================================================== model
+struct RawTensor {
+  const float* ptr;
+  std::vector<int64_t> shape;
+  long long numel() const {
+    long long n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+struct PackedW {
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+  int rows = 0;  // Cout total per tap
+  int K = 0;     // Cin
+  int taps = 1;
+  std::map<int, std::pair<CUtensorMap, CUtensorMap>> maps;  // by box rows (BN)
+};
+
+struct ResSpec {
+  std::string name;
+  int cin, cout, emb_off;
+};
+struct Layer {
+  enum Kind { CONV_IN, RES, ST, DOWN, UP } kind;
+  std::string name;
+  int cin = 0, cout = 0, emb_off = 0;
+};
+struct BlockSpec {
+  std::vector<Layer> layers;
+};
+
+enum OpKind {
+  OP_GEMM, OP_CONV_IN, OP_GN_STATS, OP_GN_FINALIZE, OP_ACT_SPLIT, OP_LN_SPLIT, OP_GEGLU, OP_SOFTMAX,
+  OP_TIME_SIN, OP_SMALL_LINEAR, OP_CONV_OUT, OP_MEMSET
+};
+enum ExtSlot { EXT_NONE = 0, EXT_X, EXT_T, EXT_COND, EXT_OUT };
+
+struct Op {
+  OpKind kind;
+  int ext = EXT_NONE;
+  int bn = 0;
+  GemmParams g;
+  const void* p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* o[2] = {nullptr, nullptr};
+  long long i[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float f = 0.f;
+};
+
+struct Plan {
+  int B = 0, n_cond = 0, H = 0, W = 0;
+  void* workspace = nullptr;
+  size_t bytes = 0;
+  std::vector<Op> ops;
+};
+
+}  // namespace pf
+
+struct pf_unet {
+  pf_unet_cfg cfg;
+  int num_sms = 148;
+  bool finalized = false;
+  std::unordered_map<std::string, pf::RawTensor> raw;
+  std::unordered_map<std::string, pf::PackedW> packed;
+  std::unordered_map<std::string, float*> fvecs;
+  std::vector<void*> owned;  // device allocations owned by the model
+  std::vector<pf::BlockSpec> input_blocks, output_blocks;
+  pf::BlockSpec middle;
+  std::vector<int> input_block_channels;
+  int emb_total = 0;  // sum of ResBlock out channels (rows of the concatenated emb projection)
+  int n_st = 0;       // number of SpatialTransformer layers
+  std::vector<std::unique_ptr<pf::Plan>> plans;
+  pf::Plan* last_plan = nullptr;
+  cudaStream_t pack_stream = nullptr;
+  bool packing = false;
+};
+
+namespace pf {
+
+static thread_local std::string g_err;
+
+template <class F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  } catch (...) {
+    g_err = "unknown error";
+    return 2;
+  }
+}
+
+// ----------------------------------------------------------------------------- module graph
+static void build_graph(pf_unet* m) {
+  const pf_unet_cfg& c = m->cfg;
+  PF_CHECK(c.n_levels >= 1 && c.n_levels <= 8, "n_levels out of range");
+  int ch = c.channels;
+  int res_count = 0;
+  auto add_res = [&](BlockSpec& b, const std::string& name, int cin, int cout) {
+    Layer l;
+    l.kind = Layer::RES;
+    l.name = name;
+    l.cin = cin;
+    l.cout = cout;
+    l.emb_off = m->emb_total;
+    m->emb_total += cout;
+    ++res_count;
+    b.layers.push_back(l);
+  };
+  auto add_simple = [&](BlockSpec& b, Layer::Kind k, const std::string& name, int cin, int cout) {
+    Layer l;
+    l.kind = k;
+    l.name = name;
+    l.cin = cin;
+    l.cout = cout;
+    if (k == Layer::ST) ++m->n_st;
+    b.layers.push_back(l);
+  };
+  {
+    BlockSpec b;
+    add_simple(b, Layer::CONV_IN, "input_blocks.0.0", c.in_channels, ch);
+    m->input_blocks.push_back(b);
+    m->input_block_channels.push_back(ch);
+  }
+  for (int lvl = 0; lvl < c.n_levels; ++lvl) {
+    const int cl = c.channels * c.channel_multipliers[lvl];
+    for (int r = 0; r < c.n_res_blocks; ++r) {
+      BlockSpec b;
+      const std::string base = "input_blocks." + std::to_string(m->input_blocks.size());
+      add_res(b, base + ".0", ch, cl);
+      ch = cl;
+      if (c.attention_levels[lvl]) add_simple(b, Layer::ST, base + ".1", ch, ch);
+      m->input_blocks.push_back(b);
+      m->input_block_channels.push_back(ch);
+    }
+    if (lvl != c.n_levels - 1) {
+      BlockSpec b;
+      const std::string base = "input_blocks." + std::to_string(m->input_blocks.size());
+      add_simple(b, Layer::DOWN, base + ".0", ch, ch);
+      m->input_blocks.push_back(b);
+      m->input_block_channels.push_back(ch);
+    }
+  }
+  add_res(m->middle, "middle_block.0", ch, ch);
+  add_simple(m->middle, Layer::ST, "middle_block.1", ch, ch);
+  add_res(m->middle, "middle_block.2", ch, ch);
+
+  std::vector<int> ibc = m->input_block_channels;
+  for (int lvl = c.n_levels - 1; lvl >= 0; --lvl) {
+    const int cl = c.channels * c.channel_multipliers[lvl];
+    for (int j = 0; j <= c.n_res_blocks; ++j) {
+      BlockSpec b;
+      const std::string base = "output_blocks." + std::to_string(m->output_blocks.size());
+      const int skip = ibc.back();
+      ibc.pop_back();
+      int idx = 0;
+      add_res(b, base + "." + std::to_string(idx++), ch + skip, cl);
+      ch = cl;
+      if (c.attention_levels[lvl]) add_simple(b, Layer::ST, base + "." + std::to_string(idx++), ch, ch);
+      if (lvl != 0 && j == c.n_res_blocks)
+        add_simple(b, Layer::UP, base + "." + std::to_string(idx++), ch, ch);
+      m->output_blocks.push_back(b);
+    }
+  }
+  PF_CHECK(ch == c.channels, "graph construction: final channel count mismatch");
+}
+
+// ----------------------------------------------------------------------------- weight access
+static void* dev_alloc(pf_unet* m, size_t bytes) {
+  void* p = nullptr;
+  PF_CUDA(cudaMalloc(&p, bytes ? bytes : 4));
+  m->owned.push_back(p);
+  return p;
+}
+
+static const RawTensor& raw(pf_unet* m, const std::string& name) {
+  auto it = m->raw.find(name);
+  PF_CHECK(it != m->raw.end(), "missing weight '%s'", name.c_str());
+  return it->second;
+}
+
+// fp32 vector/matrix copy owned by the model
+static const float* F(pf_unet* m, const std::string& name) {
+  auto it = m->fvecs.find(name);
+  if (it != m->fvecs.end()) return it->second;
+  PF_CHECK(m->packing, "weight '%s' was not prepared by pf_unet_finalize", name.c_str());
+  const RawTensor& r = raw(m, name);
+  float* d = static_cast<float*>(dev_alloc(m, r.numel() * sizeof(float)));
+  PF_CUDA(cudaMemcpyAsync(d, r.ptr, r.numel() * sizeof(float), cudaMemcpyDeviceToDevice, m->pack_stream));
+  m->fvecs[name] = d;
+  return d;
+}
+
+// elementwise sum of two (or one) named vectors
+static const float* Fsum(pf_unet* m, const std::string& a, const std::string& b) {
+  const std::string key = "sum:" + a + "+" + b;
+  auto it = m->fvecs.find(key);
+  if (it != m->fvecs.end()) return it->second;
+  PF_CHECK(m->packing, "bias sum '%s' was not prepared by pf_unet_finalize", key.c_str());
+  const RawTensor& ra = raw(m, a);
+  const RawTensor& rb = raw(m, b);
+  PF_CHECK(ra.numel() == rb.numel(), "bias size mismatch %s / %s", a.c_str(), b.c_str());
+  float* d = static_cast<float*>(dev_alloc(m, ra.numel() * sizeof(float)));
+  launch_vec_add(ra.ptr, rb.ptr, d, static_cast<int>(ra.numel()), m->pack_stream);
+  m->fvecs[key] = d;
+  return d;
+}
+
+// concatenation (along dim 0) of named tensors, optionally summed with a second list
+static const float* Fcat(pf_unet* m, const std::string& key, const std::vector<std::string>& names,
+                         const std::vector<std::string>* add_names) {
+  auto it = m->fvecs.find(key);
+  if (it != m->fvecs.end()) return it->second;
+  PF_CHECK(m->packing, "'%s' was not prepared by pf_unet_finalize", key.c_str());
+  long long total = 0;
+  for (auto& n : names) total += raw(m, n).numel();
+  float* d = static_cast<float*>(dev_alloc(m, total * sizeof(float)));
+  long long off = 0;
+  for (size_t i = 0; i < names.size(); ++i) {
+    const RawTensor& r = raw(m, names[i]);
+    const float* b = add_names ? raw(m, (*add_names)[i]).ptr : nullptr;
+    if (add_names) PF_CHECK(raw(m, (*add_names)[i]).numel() == r.numel(), "cat/add size mismatch");
+    launch_vec_add(r.ptr, b, d + off, static_cast<int>(r.numel()), m->pack_stream);
+    off += r.numel();
+  }
+  m->fvecs[key] = d;
+  return d;
+}
+
+// split-bf16 tap-major packed GEMM weight: concatenation of `names` along Cout
+static PackedW& W(pf_unet* m, const std::string& key, const std::vector<std::string>& names) {
+  auto it = m->packed.find(key);
+  if (it != m->packed.end()) return it->second;
+  PF_CHECK(m->packing, "packed weight '%s' was not prepared by pf_unet_finalize", key.c_str());
+  int rows = 0, K = -1, taps = -1;
+  for (auto& n : names) {
+    const RawTensor& r = raw(m, n);
+    PF_CHECK(r.shape.size() == 2 || r.shape.size() == 4, "weight %s: expected 2-D or 4-D", n.c_str());
+    const int k = static_cast<int>(r.shape[1]);
+    const int t = r.shape.size() == 4 ? static_cast<int>(r.shape[2] * r.shape[3]) : 1;
+    PF_CHECK(K < 0 || (K == k && taps == t), "weight %s: incompatible shapes in concat", n.c_str());
+    K = k;
+    taps = t;
+    rows += static_cast<int>(r.shape[0]);
+  }
+  PF_CHECK(K % 64 == 0, "weight %s: Cin=%d must be a multiple of 64", key.c_str(), K);
+  PF_CHECK(rows % 64 == 0, "weight %s: Cout=%d must be a multiple of 64", key.c_str(), rows);
+  PackedW pw;
+  pw.rows = rows;
+  pw.K = K;
+  pw.taps = taps;
+  const size_t bytes = static_cast<size_t>(taps) * rows * K * sizeof(bf16);
+  pw.hi = static_cast<bf16*>(dev_alloc(m, bytes));
+  pw.lo = static_cast<bf16*>(dev_alloc(m, bytes));
+  int row0 = 0;
+  for (auto& n : names) {
+    const RawTensor& r = raw(m, n);
+    launch_pack_weight(r.ptr, pw.hi, pw.lo, static_cast<int>(r.shape[0]), K, taps, rows, row0,
+                       m->pack_stream);
+    row0 += static_cast<int>(r.shape[0]);
+  }
+  return m->packed[key] = pw;
+}
+
+static const std::pair<CUtensorMap, CUtensorMap>& wmaps(PackedW& w, int bn, bool dry) {
+  auto it = w.maps.find(bn);
+  if (it != w.maps.end()) return it->second;
+  std::pair<CUtensorMap, CUtensorMap> mp;
+  memset(&mp, 0, sizeof mp);
+  if (!dry) {
+    mp.first = make_map_2d(w.hi, w.K, static_cast<long long>(w.taps) * w.rows, bn);
+    mp.second = make_map_2d(w.lo, w.K, static_cast<long long>(w.taps) * w.rows, bn);
+    return w.maps[bn] = mp;
+  }
+  static std::pair<CUtensorMap, CUtensorMap> dummy;
+  return dummy;
+}
+
+// =================================================================================== plan builder
+struct T {  // fp32 NHWC activation
+  float* p = nullptr;
+  int C = 0, H = 0, W = 0;
+};
+
+struct Builder {
+  pf_unet* m;
+  Plan* plan;
+  Arena arena;
+  bool dry;
+  int B, n_cond;
+  double* gn_pool = nullptr;
+  size_t gn_pool_doubles = 0, gn_used = 0;
+  const float* emb_all = nullptr;  // [B, emb_total]
+  const float* cross_v = nullptr;  // [B, n_st * d_attn]  (n_cond == 1)
+  int st_index = 0;
+  const float* cond_ext = nullptr;
+
+  Builder(pf_unet* m_, Plan* p_, char* base, bool dry_, int B_, int nc)
+      : m(m_), plan(p_), arena(base), dry(dry_), B(B_), n_cond(nc) {}
+
+  template <class X>
+  X* alloc(size_t count) {
+    return static_cast<X*>(arena.alloc(count * sizeof(X)));
+  }
+  Split alloc_split(size_t count) {
+    Split s;
+    s.hi = alloc<bf16>(count);
+    s.lo = alloc<bf16>(count);
+    return s;
+  }
+  void free_split(Split& s) {
+    arena.free(s.hi);
+    arena.free(s.lo);
+    s.hi = s.lo = nullptr;
+  }
+  Op& push(OpKind k) {
+    plan->ops.emplace_back();
+    Op& op = plan->ops.back();
+    op.kind = k;
+    memset(&op.g, 0, sizeof op.g);
+    return op;
+  }
+
+  // ---------------------------------------------------------------- elementwise emitters
+  void gn_scale_shift(const T& x0, const T* x1, const std::string& gname, const std::string& bname,
+                      float eps, float*& scale, float*& shift) {
+    const int C = x0.C + (x1 ? x1->C : 0);
+    const int HW = x0.H * x0.W;
+    PF_CHECK(C % 32 == 0, "GroupNorm channels %d not divisible by 32", C);
+    double* acc = gn_pool + gn_used;
+    gn_used += static_cast<size_t>(B) * C * 2;
+    PF_CHECK(dry || gn_used <= gn_pool_doubles, "GN accumulator pool overflow");
+    auto stats = [&](const T& x, int coff) {
+      PF_CHECK(x.C % 4 == 0 && 256 % (x.C / 4) == 0 && x.C <= 256, "gn_stats: unsupported C=%d", x.C);
+      Op& op = push(OP_GN_STATS);
+      op.p[0] = x.p;
+      op.o[0] = acc;
+      op.i[0] = B; op.i[1] = HW; op.i[2] = x.C; op.i[3] = C; op.i[4] = coff;
+    };
+    stats(x0, 0);
+    if (x1) stats(*x1, x0.C);
+    scale = alloc<float>(static_cast<size_t>(B) * C);
+    shift = alloc<float>(static_cast<size_t>(B) * C);
+    Op& op = push(OP_GN_FINALIZE);
+    op.p[0] = acc; op.p[1] = F(m, gname); op.p[2] = F(m, bname);
+    op.o[0] = scale; op.o[1] = shift;
+    op.i[0] = B; op.i[1] = HW; op.i[2] = C; op.i[3] = 32;
+    op.f = eps;
+  }
+
+  // split-bf16 operand of act(GN(cat(x0, x1)))
+  Split act_split(const T& x0, const T* x1, const float* scale, const float* shift, bool silu,
+                  int layout) {
+    const int C = x0.C + (x1 ? x1->C : 0);
+    size_t count = static_cast<size_t>(B) * x0.H * x0.W * C;
+    if (layout == XF_UP2) count *= 4;
+    Split s = alloc_split(count);
+    Op& op = push(OP_ACT_SPLIT);
+    op.p[0] = x0.p; op.p[1] = x1 ? x1->p : nullptr; op.p[2] = scale; op.p[3] = shift;
+    op.o[0] = s.hi; op.o[1] = s.lo;
+    op.i[0] = x0.C; op.i[1] = x1 ? x1->C : 0; op.i[2] = silu; op.i[3] = layout;
+    op.i[4] = B; op.i[5] = x0.H; op.i[6] = x0.W;
+    return s;
+  }
+
+  Split ln_split(const float* src, long long rows, int C, const std::string& prefix) {
+    PF_CHECK(C % 128 == 0 && C <= 512, "LayerNorm width %d unsupported", C);
+    Split s = alloc_split(static_cast<size_t>(rows) * C);
+    Op& op = push(OP_LN_SPLIT);
+    op.p[0] = src; op.p[1] = F(m, prefix + ".weight"); op.p[2] = F(m, prefix + ".bias");
+    op.o[0] = s.hi; op.o[1] = s.lo;
+    op.i[0] = rows; op.i[1] = C;
+    op.f = 1e-5f;
+    return s;
+  }
+
+  void small_linear(const float* in, long long ld_in, const float* Wt, const float* bias, float* out,
+                    long long ld_out, int N, int K, int in_act, int ext = EXT_NONE) {
+    Op& op = push(OP_SMALL_LINEAR);
+    op.ext = ext;
+    op.p[0] = in; op.p[1] = Wt; op.p[2] = bias;
+    op.o[0] = out;
+    op.i[0] = ld_in; op.i[1] = ld_out; op.i[2] = B; op.i[3] = N; op.i[4] = K; op.i[5] = in_act;
+  }
+
+  // ---------------------------------------------------------------- GEMM emitters
+  struct ASrc {
+    Split buf;
+    int C;        // channels of the operand tensor (TMA dim 0)
+    int W, H, N;  // TMA dims 1..3
+    int kind;     // 0 = 1x1 (no shift), 1 = 3x3, 2 = 3x3 stride-2 over S2D planes
+  };
+
+  void fill_seg(GemmSeg& sg, const ASrc& a, PackedW& w, int bn, int box_w, int box_h) {
+    memset(&sg, 0, sizeof sg);
+    if (a.kind == 0) fill_taps_1x1(sg);
+    else if (a.kind == 1) fill_taps_3x3(sg);
+    else fill_taps_3x3_s2d(sg);
+    PF_CHECK(sg.ntaps == w.taps, "tap count mismatch (%d vs %d)", sg.ntaps, w.taps);
+    PF_CHECK(a.C == w.K, "GEMM K mismatch: operand has %d channels, weight expects %d", a.C, w.K);
+    sg.kb_per_tap = a.C / 64;
+    sg.b_tap_stride = w.rows;
+    if (!dry) {
+      sg.a_hi = make_map_4d(a.buf.hi, a.C, a.W, a.H, a.N, box_w, box_h);
+      sg.a_lo = make_map_4d(a.buf.lo, a.C, a.W, a.H, a.N, box_w, box_h);
+      auto& mp = wmaps(w, bn, dry);
+      sg.b_hi = mp.first;
+      sg.b_lo = mp.second;
+    }
+  }
+
+  // conv / linear GEMM over B images of Ho x Wo output pixels.
+  // seg1 (optional) is a 1x1 segment accumulated into the same tile (ResBlock skip conv).
+  Op& conv_gemm(const ASrc& a0, PackedW& w0, const ASrc* a1, PackedW* w1, int Ho, int Wo, int Cout,
+                int row0 = 0) {
+    const int bn = choose_bn(Cout);
+    const int box_w = choose_box_w(Wo);
+    PF_CHECK(128 % box_w == 0 && Wo % box_w == 0, "unsupported width %d", Wo);
+    const int box_h = 128 / box_w;
+    PF_CHECK(Ho % box_h == 0, "unsupported height %d for width %d", Ho, Wo);
+    Op& op = push(OP_GEMM);
+    op.bn = bn;
+    GemmParams& g = op.g;
+    fill_seg(g.seg[0], a0, w0, bn, box_w, box_h);
+    g.seg[0].b_row0 = row0;
+    g.nseg = 1;
+    if (a1) {
+      fill_seg(g.seg[1], *a1, *w1, bn, box_w, box_h);
+      g.nseg = 2;
+    }
+    g.nstages = gemm_default_stages(bn);
+    g.tiles_x = Wo / box_w;
+    g.tiles_per_img = g.tiles_x * (Ho / box_h);
+    g.box_w = box_w;
+    g.box_h = box_h;
+    g.zdiv = 1;
+    g.n_tiles = Cout / bn;
+    g.m_tiles = B * g.tiles_per_img;
+    g.z_count = 1;
+    return op;
+  }
+
+  void out_f32(Op& op, float* out, int ldc, const float* addvec, long long addvec_ld,
+               const float* resid, long long ldr) {
+    op.g.mode = OUT_F32;
+    op.g.out = out;
+    op.g.ldc = ldc;
+    op.g.addvec = addvec;
+    op.g.addvec_ld = addvec_ld;
+    op.g.resid = resid;
+    op.g.ldr = ldr;
+  }
+
+  // ---------------------------------------------------------------- layers
+  T res_block(const Layer& L, const T& x0, const T* x1) {
+    const int C = x0.C + (x1 ? x1->C : 0);
+    PF_CHECK(C == L.cin, "ResBlock %s: got %d input channels, expected %d", L.name.c_str(), C, L.cin);
+    const int H = x0.H, Wd = x0.W;
+    const size_t npix = static_cast<size_t>(B) * H * Wd;
+    float *sc, *sh;
+    gn_scale_shift(x0, x1, L.name + ".in_layers.0.weight", L.name + ".in_layers.0.bias", 1e-5f, sc, sh);
+    Split a1 = act_split(x0, x1, sc, sh, true, XF_SAME);
+    arena.free(sc);
+    arena.free(sh);
+    T h1;
+    h1.C = L.cout; h1.H = H; h1.W = Wd;
+    h1.p = alloc<float>(npix * L.cout);
+    {
+      PackedW& w = W(m, L.name + ".in_layers.2.weight", {L.name + ".in_layers.2.weight"});
+      ASrc a{a1, C, Wd, H, B, 1};
+      Op& op = conv_gemm(a, w, nullptr, nullptr, H, Wd, L.cout);
+      // addvec = Linear(SiLU(t_emb)) + emb bias + conv1 bias  (unet.py:308-316)
+      out_f32(op, h1.p, L.cout, emb_all + L.emb_off, m->emb_total, nullptr, 0);
+    }
+    free_split(a1);
+    gn_scale_shift(h1, nullptr, L.name + ".out_layers.0.weight", L.name + ".out_layers.0.bias", 1e-5f, sc, sh);
+    Split a2 = act_split(h1, nullptr, sc, sh, true, XF_SAME);
+    arena.free(sc);
+    arena.free(sh);
+    arena.free(h1.p);
+    T y;
+    y.C = L.cout; y.H = H; y.W = Wd;
+    y.p = alloc<float>(npix * L.cout);
+    PackedW& w2 = W(m, L.name + ".out_layers.3.weight", {L.name + ".out_layers.3.weight"});
+    ASrc s2{a2, L.cout, Wd, H, B, 1};
+    if (L.cin != L.cout) {
+      Split a3 = act_split(x0, x1, nullptr, nullptr, false, XF_SAME);
+      PackedW& ws = W(m, L.name + ".skip_connection.weight", {L.name + ".skip_connection.weight"});
+      ASrc s3{a3, C, Wd, H, B, 0};
+      Op& op = conv_gemm(s2, w2, &s3, &ws, H, Wd, L.cout);
+      out_f32(op, y.p, L.cout, Fsum(m, L.name + ".out_layers.3.bias", L.name + ".skip_connection.bias"),
+              0, nullptr, 0);
+      free_split(a3);
+    } else {
+      PF_CHECK(!x1, "identity skip with concatenated input");
+      Op& op = conv_gemm(s2, w2, nullptr, nullptr, H, Wd, L.cout);
+      out_f32(op, y.p, L.cout, F(m, L.name + ".out_layers.3.bias"), 0, x0.p, x0.C);
+    }
+    free_split(a2);
+    return y;
+  }
+
+  // batched attention core: q (cols qcol0 + h*64 of a [B*N, ldq] split tensor) against
+  // k ([B*Nk, ldk] split, cols kcol0 + h*64) and v^T ([B*heads*64, Nk] split) -> O split [B*N, ldo]
+  void attention_core(const Split& q, int ldq, int qcol0, const Split& k, int ldk, int kcol0,
+                      const Split& vt, int N, int Nq_w, int Nq_h, int Nk, int heads, Split& o,
+                      int ldo) {
+    const int Z = B * heads;
+    PF_CHECK(Nk % 128 == 0 && Nk <= 1024, "attention: unsupported key count %d", Nk);
+    float* S = alloc<float>(static_cast<size_t>(Z) * N * Nk);
+    {
+      const int bn = choose_bn(Nk);
+      const int box_w = choose_box_w(Nq_w), box_h = 128 / box_w;
+      Op& op = push(OP_GEMM);
+      op.bn = bn;
+      GemmParams& g = op.g;
+      GemmSeg& sg = g.seg[0];
+      memset(&sg, 0, sizeof sg);
+      fill_taps_1x1(sg);
+      sg.kb_per_tap = 1;  // d_head = 64
+      sg.a_col0 = qcol0;
+      sg.a_img_zb = 1;    // image = batch index
+      sg.a_col_zh = 64;   // head -> channel offset
+      sg.b_row_zb = Nk;
+      sg.b_col0 = kcol0;
+      sg.b_col_zh = 64;
+      if (!dry) {
+        sg.a_hi = make_map_4d(q.hi, ldq, Nq_w, Nq_h, B, box_w, box_h);
+        sg.a_lo = make_map_4d(q.lo, ldq, Nq_w, Nq_h, B, box_w, box_h);
+        sg.b_hi = make_map_2d(k.hi, ldk, static_cast<long long>(B) * Nk, bn);
+        sg.b_lo = make_map_2d(k.lo, ldk, static_cast<long long>(B) * Nk, bn);
+      }
+      g.nseg = 1;
+      g.nstages = gemm_default_stages(bn);
+      g.tiles_x = Nq_w / box_w;
+      g.tiles_per_img = N / 128;
+      g.box_w = box_w;
+      g.box_h = box_h;
+      g.zdiv = heads;
+      g.n_tiles = Nk / bn;
+      g.m_tiles = N / 128;
+      g.z_count = Z;
+      g.mode = OUT_F32;
+      g.out = S;
+      g.ldc = Nk;
+      g.out_zb = static_cast<long long>(heads) * N * Nk;
+      g.out_zh = static_cast<long long>(N) * Nk;
+    }
+    Split P = alloc_split(static_cast<size_t>(Z) * N * Nk);
+    {
+      Op& op = push(OP_SOFTMAX);
+      op.p[0] = S;
+      op.o[0] = P.hi; op.o[1] = P.lo;
+      op.i[0] = static_cast<long long>(Z) * N; op.i[1] = Nk;
+      op.f = 0.125f;  // d_head ** -0.5 with d_head = 64 (unet_attention.py:157)
+    }
+    arena.free(S);
+    {
+      Op& op = push(OP_GEMM);
+      op.bn = 64;
+      GemmParams& g = op.g;
+      GemmSeg& sg = g.seg[0];
+      memset(&sg, 0, sizeof sg);
+      fill_taps_1x1(sg);
+      sg.kb_per_tap = Nk / 64;
+      sg.a_img_zb = heads;
+      sg.a_img_zh = 1;
+      sg.b_row_zb = heads * 64;
+      sg.b_row_zh = 64;
+      if (!dry) {
+        sg.a_hi = make_map_4d(P.hi, Nk, N, 1, Z, 128, 1);
+        sg.a_lo = make_map_4d(P.lo, Nk, N, 1, Z, 128, 1);
+        sg.b_hi = make_map_2d(vt.hi, Nk, static_cast<long long>(Z) * 64, 64);
+        sg.b_lo = make_map_2d(vt.lo, Nk, static_cast<long long>(Z) * 64, 64);
+      }
+      g.nseg = 1;
+      g.nstages = gemm_default_stages(64);
+      g.tiles_x = N / 128;
+      g.tiles_per_img = N / 128;
+      g.box_w = 128;
+      g.box_h = 1;
+      g.zdiv = heads;
+      g.n_tiles = 1;
+      g.m_tiles = N / 128;
+      g.z_count = Z;
+      g.mode = OUT_SPLIT;
+      g.out_hi = o.hi;
+      g.out_lo = o.lo;
+      g.ldc = ldo;
+      g.out_zb = static_cast<long long>(N) * ldo;
+      g.out_zh = 64;
+    }
+    free_split(P);
+  }
+
+  T spatial_transformer(const Layer& L, const T& x) {
+    const pf_unet_cfg& c = m->cfg;
+    const int C = x.C, H = x.H, Wd = x.W, N = H * Wd;
+    const int heads = c.n_heads;
+    PF_CHECK(C == heads * 64, "SpatialTransformer %s: d_head must be 64 (C=%d, heads=%d)",
+             L.name.c_str(), C, heads);
+    PF_CHECK(N % 128 == 0, "SpatialTransformer: %d tokens per image is not a multiple of 128", N);
+    const long long rows = static_cast<long long>(B) * N;
+    const int sti = st_index++;
+    float *sc, *sh;
+    gn_scale_shift(x, nullptr, L.name + ".norm.weight", L.name + ".norm.bias", 1e-6f, sc, sh);
+    Split a = act_split(x, nullptr, sc, sh, false, XF_SAME);
+    arena.free(sc);
+    arena.free(sh);
+    float* t0 = alloc<float>(rows * C);
+    {
+      PackedW& w = W(m, L.name + ".proj_in.weight", {L.name + ".proj_in.weight"});
+      ASrc s{a, C, Wd, H, B, 0};
+      Op& op = conv_gemm(s, w, nullptr, nullptr, H, Wd, C);
+      out_f32(op, t0, C, F(m, L.name + ".proj_in.bias"), 0, nullptr, 0);
+    }
+    free_split(a);
+
+    for (int li = 0; li < c.tf_layers; ++li) {
+      const std::string tb = L.name + ".transformer_blocks." + std::to_string(li);
+      // ---- self attention: x = attn1(norm1(x)) + x
+      Split l1 = ln_split(t0, rows, C, tb + ".norm1");
+      Split qk = alloc_split(rows * 2 * C);
+      Split vt = alloc_split(rows * C);
+      ASrc sl{l1, C, Wd, H, B, 0};
+      {
+        PackedW& w = W(m, tb + ".attn1.qkv", {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight",
+                                             tb + ".attn1.to_v.weight"});
+        Op& op = conv_gemm(sl, w, nullptr, nullptr, H, Wd, 2 * C, 0);
+        op.g.mode = OUT_SPLIT;
+        op.g.out_hi = qk.hi; op.g.out_lo = qk.lo; op.g.ldc = 2 * C;
+        Op& ov = conv_gemm(sl, w, nullptr, nullptr, H, Wd, C, 2 * C);
+        ov.g.mode = OUT_SPLIT_T;
+        ov.g.out_hi = vt.hi; ov.g.out_lo = vt.lo; ov.g.ldc = N;
+        ov.g.out_img = static_cast<long long>(C) * N;
+      }
+      free_split(l1);
+      Split o = alloc_split(rows * C);
+      attention_core(qk, 2 * C, 0, qk, 2 * C, C, vt, N, Wd, H, N, heads, o, C);
+      free_split(qk);
+      free_split(vt);
+      float* x1 = alloc<float>(rows * C);
+      ASrc so{o, C, Wd, H, B, 0};
+      PackedW& wo = W(m, tb + ".attn1.to_out.0.weight", {tb + ".attn1.to_out.0.weight"});
+      // always prepare both cross-attention variants while packing
+      if (m->packing || n_cond == 1) {
+        Fsum(m, tb + ".attn1.to_out.0.bias", tb + ".attn2.to_out.0.bias");
+        F(m, tb + ".attn2.to_out.0.weight");
+      }
+      if (m->packing || n_cond != 1) {
+        F(m, tb + ".attn1.to_out.0.bias");
+        F(m, tb + ".attn2.to_out.0.bias");
+        W(m, tb + ".attn2.to_q.weight", {tb + ".attn2.to_q.weight"});
+        if (c.d_cond % 64 == 0) {
+          W(m, tb + ".attn2.to_k.weight", {tb + ".attn2.to_k.weight"});
+          W(m, tb + ".attn2.to_v.weight", {tb + ".attn2.to_v.weight"});
+        }
+        W(m, tb + ".attn2.to_out.0.weight", {tb + ".attn2.to_out.0.weight"});
+      }
+      float* xattn = nullptr;
+      if (n_cond == 1) {
+        // softmax over a single key == 1: attn2(.) == to_out(to_v(cond)) for every token.
+        // cv[b] = Wout2 . v[b] + bout2 + bout1 is added in the attn1 out-projection epilogue.
+        float* cv = alloc<float>(static_cast<size_t>(B) * C);
+        small_linear(cross_v + static_cast<size_t>(sti * c.tf_layers + li) * C,
+                     static_cast<long long>(m->n_st) * c.tf_layers * C,
+                     F(m, tb + ".attn2.to_out.0.weight"),
+                     Fsum(m, tb + ".attn1.to_out.0.bias", tb + ".attn2.to_out.0.bias"), cv, C, C, C, 0);
+        Op& op = conv_gemm(so, wo, nullptr, nullptr, H, Wd, C);
+        out_f32(op, x1, C, cv, C, t0, C);
+        free_split(o);
+        arena.free(cv);
+        xattn = x1;
+      } else {
+        Op& op = conv_gemm(so, wo, nullptr, nullptr, H, Wd, C);
+        out_f32(op, x1, C, F(m, tb + ".attn1.to_out.0.bias"), 0, t0, C);
+        free_split(o);
+        // ---- cross attention: x = attn2(norm2(x), cond) + x
+        PF_CHECK(n_cond % 128 == 0 && n_cond <= 1024 && c.d_cond % 64 == 0,
+                 "cross-attention supports n_cond == 1 or n_cond %% 128 == 0 (<= 1024) with d_cond %% 64 == 0; "
+                 "got n_cond=%d d_cond=%d", n_cond, c.d_cond);
+        Split l2 = ln_split(x1, rows, C, tb + ".norm2");
+        Split q2 = alloc_split(rows * C);
+        {
+          ASrc s{l2, C, Wd, H, B, 0};
+          Op& opq = conv_gemm(s, W(m, tb + ".attn2.to_q.weight", {}), nullptr, nullptr, H, Wd, C);
+          opq.g.mode = OUT_SPLIT;
+          opq.g.out_hi = q2.hi; opq.g.out_lo = q2.lo; opq.g.ldc = C;
+        }
+        free_split(l2);
+        // cond -> split operand [B, 1, n_cond, d_cond]
+        T ct;
+        ct.p = const_cast<float*>(cond_ext);
+        ct.C = c.d_cond; ct.H = 1; ct.W = n_cond;
+        Split cs = act_split(ct, nullptr, nullptr, nullptr, false, XF_SAME);
+        plan->ops.back().ext = EXT_COND;
+        const long long crow = static_cast<long long>(B) * n_cond;
+        Split k2 = alloc_split(crow * C);
+        Split v2t = alloc_split(crow * C);
+        {
+          ASrc s{cs, c.d_cond, n_cond, 1, B, 0};
+          Op& opk = conv_gemm(s, W(m, tb + ".attn2.to_k.weight", {}), nullptr, nullptr, 1, n_cond, C);
+          opk.g.mode = OUT_SPLIT;
+          opk.g.out_hi = k2.hi; opk.g.out_lo = k2.lo; opk.g.ldc = C;
+          Op& opv = conv_gemm(s, W(m, tb + ".attn2.to_v.weight", {}), nullptr, nullptr, 1, n_cond, C);
+          opv.g.mode = OUT_SPLIT_T;
+          opv.g.out_hi = v2t.hi; opv.g.out_lo = v2t.lo; opv.g.ldc = n_cond;
+          opv.g.out_img = static_cast<long long>(C) * n_cond;
+        }
+        free_split(cs);
+        Split o2 = alloc_split(rows * C);
+        attention_core(q2, C, 0, k2, C, 0, v2t, N, Wd, H, n_cond, heads, o2, C);
+        free_split(q2);
+        free_split(k2);
+        free_split(v2t);
+        float* x2 = alloc<float>(rows * C);
+        ASrc s2{o2, C, Wd, H, B, 0};
+        Op& op2 = conv_gemm(s2, W(m, tb + ".attn2.to_out.0.weight", {}), nullptr, nullptr, H, Wd, C);
+        out_f32(op2, x2, C, F(m, tb + ".attn2.to_out.0.bias"), 0, x1, C);
+        free_split(o2);
+        arena.free(x1);
+        xattn = x2;
+      }
+      arena.free(t0);
+      // ---- feed forward: x = ff(norm3(x)) + x   (GeGLU, unet_attention.py:296-333)
+      Split l3 = ln_split(xattn, rows, C, tb + ".norm3");
+      const int Fh = 4 * C;
+      float* gg = alloc<float>(rows * 2 * Fh);
+      {
+        ASrc s{l3, C, Wd, H, B, 0};
+        Op& op = conv_gemm(s, W(m, tb + ".ff.net.0.proj.weight", {tb + ".ff.net.0.proj.weight"}),
+                           nullptr, nullptr, H, Wd, 2 * Fh);
+        out_f32(op, gg, 2 * Fh, F(m, tb + ".ff.net.0.proj.bias"), 0, nullptr, 0);
+      }
+      free_split(l3);
+      Split e = alloc_split(rows * Fh);
+      {
+        Op& op = push(OP_GEGLU);
+        op.p[0] = gg;
+        op.o[0] = e.hi; op.o[1] = e.lo;
+        op.i[0] = rows; op.i[1] = Fh;
+      }
+      arena.free(gg);
+      float* x3 = alloc<float>(rows * C);
+      {
+        ASrc s{e, Fh, Wd, H, B, 0};
+        Op& op = conv_gemm(s, W(m, tb + ".ff.net.2.weight", {tb + ".ff.net.2.weight"}), nullptr,
+                           nullptr, H, Wd, C);
+        out_f32(op, x3, C, F(m, tb + ".ff.net.2.bias"), 0, xattn, C);
+      }
+      free_split(e);
+      arena.free(xattn);
+      t0 = x3;
+    }
+    // proj_out + residual
+    T tt;
+    tt.p = t0; tt.C = C; tt.H = H; tt.W = Wd;
+    Split ao = act_split(tt, nullptr, nullptr, nullptr, false, XF_SAME);
+    arena.free(t0);
+    T y;
+    y.C = C; y.H = H; y.W = Wd;
+    y.p = alloc<float>(rows * C);
+    {
+      ASrc s{ao, C, Wd, H, B, 0};
+      Op& op = conv_gemm(s, W(m, L.name + ".proj_out.weight", {L.name + ".proj_out.weight"}), nullptr,
+                         nullptr, H, Wd, C);
+      out_f32(op, y.p, C, F(m, L.name + ".proj_out.bias"), 0, x.p, C);
+    }
+    free_split(ao);
+    return y;
+  }
+
+  T down_sample(const Layer& L, const T& x) {
+    PF_CHECK(x.H % 2 == 0 && x.W % 2 == 0, "DownSample needs even dims");
+    Split a = act_split(x, nullptr, nullptr, nullptr, false, XF_S2D);
+    T y;
+    y.C = x.C; y.H = x.H / 2; y.W = x.W / 2;
+    y.p = alloc<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
+    ASrc s{a, x.C, y.W, y.H, 4 * B, 2};
+    Op& op = conv_gemm(s, W(m, L.name + ".op.weight", {L.name + ".op.weight"}), nullptr, nullptr, y.H,
+                       y.W, y.C);
+    out_f32(op, y.p, y.C, F(m, L.name + ".op.bias"), 0, nullptr, 0);
+    free_split(a);
+    return y;
+  }
+
+  T up_sample(const Layer& L, const T& x) {
+    Split a = act_split(x, nullptr, nullptr, nullptr, false, XF_UP2);
+    T y;
+    y.C = x.C; y.H = x.H * 2; y.W = x.W * 2;
+    y.p = alloc<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
+    ASrc s{a, x.C, y.W, y.H, B, 1};
+    Op& op = conv_gemm(s, W(m, L.name + ".conv.weight", {L.name + ".conv.weight"}), nullptr, nullptr,
+                       y.H, y.W, y.C);
+    out_f32(op, y.p, y.C, F(m, L.name + ".conv.bias"), 0, nullptr, 0);
+    free_split(a);
+    return y;
+  }
+
+  // ---------------------------------------------------------------- whole forward
+  void build(int H, int Wd) {
+    const pf_unet_cfg& c = m->cfg;
+    const int d_temb = c.channels * 4;
+    // GroupNorm accumulator pool: sized by a generous bound, zeroed once per forward
+    {
+      size_t doubles = 0;
+      auto count_block = [&](const BlockSpec& b) {
+        for (auto& l : b.layers) {
+          if (l.kind == Layer::RES) doubles += static_cast<size_t>(B) * (l.cin + l.cout) * 2;
+          if (l.kind == Layer::ST) doubles += static_cast<size_t>(B) * l.cin * 2;
+        }
+      };
+      for (auto& b : m->input_blocks) count_block(b);
+      count_block(m->middle);
+      for (auto& b : m->output_blocks) count_block(b);
+      doubles += static_cast<size_t>(B) * c.channels * 2;  // final norm
+      gn_pool_doubles = doubles;
+      gn_pool = alloc<double>(doubles);
+      Op& op = push(OP_MEMSET);
+      op.o[0] = gn_pool;
+      op.i[0] = static_cast<long long>(doubles * sizeof(double));
+    }
+    // ---- time embedding (unet.py:64-68, 151-169, 182) and all ResBlock emb projections
+    float* sinus = alloc<float>(static_cast<size_t>(B) * c.channels);
+    {
+      Op& op = push(OP_TIME_SIN);
+      op.ext = EXT_T;
+      op.p[1] = F(m, "__time_freqs");
+      op.o[0] = sinus;
+      op.i[0] = B; op.i[1] = c.channels / 2;
+    }
+    float* te1 = alloc<float>(static_cast<size_t>(B) * d_temb);
+    float* temb = alloc<float>(static_cast<size_t>(B) * d_temb);
+    small_linear(sinus, c.channels, F(m, "time_embed.0.weight"), F(m, "time_embed.0.bias"), te1,
+                 d_temb, d_temb, c.channels, 0);
+    small_linear(te1, d_temb, F(m, "time_embed.2.weight"), F(m, "time_embed.2.bias"), temb, d_temb,
+                 d_temb, d_temb, 1);
+    {
+      std::vector<std::string> wn, bn_, cb;
+      auto collect = [&](const BlockSpec& b) {
+        for (auto& l : b.layers)
+          if (l.kind == Layer::RES) {
+            wn.push_back(l.name + ".emb_layers.1.weight");
+            bn_.push_back(l.name + ".emb_layers.1.bias");
+            cb.push_back(l.name + ".in_layers.2.bias");
+          }
+      };
+      for (auto& b : m->input_blocks) collect(b);
+      collect(m->middle);
+      for (auto& b : m->output_blocks) collect(b);
+      const float* wcat = Fcat(m, "emb_all.weight", wn, nullptr);
+      const float* bcat = Fcat(m, "emb_all.bias", bn_, &cb);
+      float* ea = alloc<float>(static_cast<size_t>(B) * m->emb_total);
+      small_linear(temb, d_temb, wcat, bcat, ea, m->emb_total, m->emb_total, d_temb, 1);
+      emb_all = ea;
+    }
+    // ---- cross-attention value vectors for n_cond == 1
+    {
+      std::vector<std::string> vn;
+      auto collect = [&](const BlockSpec& b) {
+        for (auto& l : b.layers)
+          if (l.kind == Layer::ST)
+            for (int li = 0; li < c.tf_layers; ++li)
+              vn.push_back(l.name + ".transformer_blocks." + std::to_string(li) + ".attn2.to_v.weight");
+      };
+      for (auto& b : m->input_blocks) collect(b);
+      collect(m->middle);
+      for (auto& b : m->output_blocks) collect(b);
+      const int d_attn = c.n_heads * 64;
+      const float* wv = Fcat(m, "cross_v.weight", vn, nullptr);
+      if (n_cond == 1) {
+        const int nv = static_cast<int>(vn.size()) * d_attn;
+        float* cvall = alloc<float>(static_cast<size_t>(B) * nv);
+        small_linear(nullptr, c.d_cond, wv, nullptr, cvall, nv, nv, c.d_cond, 0, EXT_COND);
+        cross_v = cvall;
+      }
+    }
+    // ---- blocks
+    std::vector<T> skips;
+    T x;
+    auto run_block = [&](const BlockSpec& b, T xin, const T* skip) -> T {
+      T cur = xin;
+      bool first = true;
+      for (auto& l : b.layers) {
+        T nxt;
+        switch (l.kind) {
+          case Layer::CONV_IN: {
+            nxt.C = l.cout; nxt.H = H; nxt.W = Wd;
+            nxt.p = alloc<float>(static_cast<size_t>(B) * H * Wd * l.cout);
+            PF_CHECK(l.cout % 16 == 0, "first conv: channels must be a multiple of 16");
+            Op& op = push(OP_CONV_IN);
+            op.ext = EXT_X;
+            op.p[1] = F(m, l.name + ".weight"); op.p[2] = F(m, l.name + ".bias");
+            op.o[0] = nxt.p;
+            op.i[0] = B; op.i[1] = l.cin; op.i[2] = H; op.i[3] = Wd; op.i[4] = l.cout;
+            break;
+          }
+          case Layer::RES: nxt = res_block(l, cur, first ? skip : nullptr); break;
+          case Layer::ST: nxt = spatial_transformer(l, cur); break;
+          case Layer::DOWN: nxt = down_sample(l, cur); break;
+          case Layer::UP: nxt = up_sample(l, cur); break;
+        }
+        // free the consumed input unless it is the block input (owned by the caller)
+        if (!first) arena.free(cur.p);
+        cur = nxt;
+        first = false;
+      }
+      return cur;
+    };
+    for (size_t bi = 0; bi < m->input_blocks.size(); ++bi) {
+      T y = run_block(m->input_blocks[bi], x, nullptr);
+      // the block input stays alive only if it is a saved skip (it always is, except before block 0)
+      x = y;
+      skips.push_back(y);
+    }
+    {
+      T y = run_block(m->middle, x, nullptr);
+      // x (== skips.back()) is still needed as a skip
+      x = y;
+    }
+    bool x_is_skip = false;
+    for (size_t bi = 0; bi < m->output_blocks.size(); ++bi) {
+      T skip = skips.back();
+      skips.pop_back();
+      T y = run_block(m->output_blocks[bi], x, &skip);
+      if (!x_is_skip) arena.free(x.p);
+      arena.free(skip.p);
+      x = y;
+    }
+    // ---- out: GroupNorm + SiLU + conv3x3 -> NCHW (unet.py:145-149, 196)
+    {
+      float *sc, *sh;
+      gn_scale_shift(x, nullptr, "out.0.weight", "out.0.bias", 1e-5f, sc, sh);
+      PF_CHECK(c.out_channels <= 4, "out_channels > 4 unsupported by the final conv kernel");
+      Op& op = push(OP_CONV_OUT);
+      op.ext = EXT_OUT;
+      op.p[0] = x.p; op.p[1] = sc; op.p[2] = sh; op.p[3] = F(m, "out.2.weight"); op.p[4] = F(m, "out.2.bias");
+      op.i[0] = B; op.i[1] = H; op.i[2] = Wd; op.i[3] = x.C; op.i[4] = c.out_channels;
+    }
+  }
+};
+
+// =================================================================================== execution
+static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, const float* cond,
+                     float* out, cudaStream_t s) {
+  for (Op& op : plan.ops) {
+    switch (op.kind) {
+      case OP_MEMSET:
+        PF_CUDA(cudaMemsetAsync(op.o[0], 0, static_cast<size_t>(op.i[0]), s));
+        break;
+      case OP_GEMM:
+        PF_CUDA(launch_gemm(op.g, op.bn, m->num_sms, s));
+        break;
+      case OP_CONV_IN:
+        launch_conv_in(x, static_cast<const float*>(op.p[1]), static_cast<const float*>(op.p[2]),
+                       static_cast<float*>(op.o[0]), (int)op.i[0], (int)op.i[1], (int)op.i[2],
+                       (int)op.i[3], (int)op.i[4], s);
+        break;
+      case OP_GN_STATS:
+        launch_gn_stats(static_cast<const float*>(op.p[0]), static_cast<double*>(op.o[0]), (int)op.i[0],
+                        (int)op.i[1], (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
+        break;
+      case OP_GN_FINALIZE:
+        launch_gn_finalize(static_cast<const double*>(op.p[0]), static_cast<const float*>(op.p[1]),
+                           static_cast<const float*>(op.p[2]), static_cast<float*>(op.o[0]),
+                           static_cast<float*>(op.o[1]), (int)op.i[0], (int)op.i[1], (int)op.i[2],
+                           (int)op.i[3], op.f, s);
+        break;
+      case OP_ACT_SPLIT:
+        launch_act_split(op.ext == EXT_COND ? cond : static_cast<const float*>(op.p[0]), (int)op.i[0],
+                         static_cast<const float*>(op.p[1]), (int)op.i[1],
+                         static_cast<const float*>(op.p[2]), static_cast<const float*>(op.p[3]),
+                         (int)op.i[2], (int)op.i[3], static_cast<bf16*>(op.o[0]),
+                         static_cast<bf16*>(op.o[1]), (int)op.i[4], (int)op.i[5], (int)op.i[6], s);
+        break;
+      case OP_LN_SPLIT:
+        launch_ln_split(static_cast<const float*>(op.p[0]), static_cast<const float*>(op.p[1]),
+                        static_cast<const float*>(op.p[2]), op.f, static_cast<bf16*>(op.o[0]),
+                        static_cast<bf16*>(op.o[1]), op.i[0], (int)op.i[1], s);
+        break;
+      case OP_GEGLU:
+        launch_geglu_split(static_cast<const float*>(op.p[0]), static_cast<bf16*>(op.o[0]),
+                           static_cast<bf16*>(op.o[1]), op.i[0], (int)op.i[1], s);
+        break;
+      case OP_SOFTMAX:
+        launch_softmax_split(static_cast<const float*>(op.p[0]), op.f, static_cast<bf16*>(op.o[0]),
+                             static_cast<bf16*>(op.o[1]), op.i[0], (int)op.i[1], s);
+        break;
+      case OP_TIME_SIN:
+        launch_time_sinusoid(reinterpret_cast<const long long*>(t), static_cast<const float*>(op.p[1]),
+                             static_cast<float*>(op.o[0]), (int)op.i[0], (int)op.i[1], s);
+        break;
+      case OP_SMALL_LINEAR:
+        launch_small_linear(op.ext == EXT_COND ? cond : static_cast<const float*>(op.p[0]), op.i[0],
+                            static_cast<const float*>(op.p[1]), static_cast<const float*>(op.p[2]),
+                            static_cast<float*>(op.o[0]), op.i[1], (int)op.i[2], (int)op.i[3],
+                            (int)op.i[4], (int)op.i[5], s);
+        break;
+      case OP_CONV_OUT:
+        launch_conv_out(static_cast<const float*>(op.p[0]), static_cast<const float*>(op.p[1]),
+                        static_cast<const float*>(op.p[2]), static_cast<const float*>(op.p[3]),
+                        static_cast<const float*>(op.p[4]), out, (int)op.i[0], (int)op.i[1],
+                        (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
+        break;
+    }
+  }
+  PF_CUDA(cudaGetLastError());
+}
+
+static void check_geometry(pf_unet* m, int B, int n_cond, int H, int Wd) {
+  const pf_unet_cfg& c = m->cfg;
+  PF_CHECK(B >= 1, "batch must be >= 1");
+  PF_CHECK(n_cond >= 1, "n_cond must be >= 1");
+  const int down = 1 << (c.n_levels - 1);
+  PF_CHECK(H % down == 0 && Wd % down == 0, "image %dx%d not divisible by %d", H, Wd, down);
+  const int wl = Wd / down, hl = H / down;
+  PF_CHECK(wl >= 1 && (hl * wl) % 128 == 0,
+           "lowest-resolution feature map %dx%d must hold a multiple of 128 pixels", hl, wl);
+  PF_CHECK(c.channels % 64 == 0, "channels must be a multiple of 64");
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+// =================================================================================== C ABI
+extern "C" {
+
+const char* pf_last_error(void) { return g_err.c_str(); }
+const char* pf_version(void) { return "polyffusion_b200 0.1 (sm_100a, tcgen05 bf16x3)"; }
+
+int pf_unet_create(const pf_unet_cfg* cfg, pf_unet** out) {
+  return guarded([&] {
+    PF_CHECK(cfg && out, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    PF_CHECK(e == cudaSuccess && ndev > 0,
+             "no CUDA device: polyffusion_b200 has no CPU fallback (%s)", cudaGetErrorString(e));
+    std::unique_ptr<pf_unet> m(new pf_unet());
+    m->cfg = *cfg;
+    int dev = 0;
+    PF_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    PF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    PF_CHECK(prop.major == 10, "this library targets sm_100a (B200); found sm_%d%d", prop.major,
+             prop.minor);
+    m->num_sms = prop.multiProcessorCount;
+    PF_CUDA(gemm_init_attrs());
+    build_graph(m.get());
+    *out = m.release();
+  });
+}
+
+void pf_unet_destroy(pf_unet* h) {
+  if (!h) return;
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+}
+
+int pf_unet_set_weight(pf_unet* h, const char* name, const float* data, const int64_t* shape,
+                       int32_t ndim) {
+  return guarded([&] {
+    PF_CHECK(h && name && data && (shape || ndim == 0), "null argument");
+    RawTensor r;
+    r.ptr = data;
+    r.shape.assign(shape, shape + ndim);
+    h->raw[name] = r;
+    h->finalized = false;
+  });
+}
+
+int pf_unet_finalize(pf_unet* h, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(h, "null handle");
+    // drop previously packed state
+    for (void* p : h->owned) cudaFree(p);
+    h->owned.clear();
+    h->packed.clear();
+    h->fvecs.clear();
+    h->plans.clear();
+    h->last_plan = nullptr;
+    h->pack_stream = static_cast<cudaStream_t>(stream);
+    h->packing = true;
+    struct Reset {
+      pf_unet* h;
+      ~Reset() { h->packing = false; }
+    } reset{h};
+    // a dry walk of the graph touches (and therefore packs) every weight the forward needs
+    Plan scratch;
+    const int down = 1 << (h->cfg.n_levels - 1);
+    int side = 16 * down;  // lowest level 16x16 = 256 px (multiple of 128)
+    Builder b(h, &scratch, reinterpret_cast<char*>(4096), true, 1, 1);
+    b.build(side, side);
+    PF_CUDA(cudaStreamSynchronize(h->pack_stream));
+    h->raw.clear();  // caller's tensors are no longer referenced
+    h->finalized = true;
+  });
+}
+
+size_t pf_unet_workspace_bytes(pf_unet* h, int32_t batch, int32_t n_cond, int32_t height,
+                               int32_t width) {
+  size_t bytes = 0;
+  int rc = guarded([&] {
+    PF_CHECK(h && h->finalized, "model not finalized");
+    check_geometry(h, batch, n_cond, height, width);
+    Plan scratch;
+    Builder b(h, &scratch, reinterpret_cast<char*>(4096), true, batch, n_cond);
+    b.cond_ext = nullptr;
+    b.build(height, width);
+    bytes = b.arena.peak();
+  });
+  return rc == 0 ? bytes : 0;
+}
+
+int pf_unet_forward(pf_unet* h, const float* x, const int64_t* time_steps, const float* cond,
+                    int32_t batch, int32_t n_cond, int32_t height, int32_t width, float* out,
+                    void* workspace, size_t workspace_bytes, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(h && h->finalized, "model not finalized");
+    PF_CHECK(x && time_steps && cond && out && workspace, "null argument");
+    Plan* plan = nullptr;
+    for (auto& p : h->plans)
+      if (p->B == batch && p->n_cond == n_cond && p->H == height && p->W == width &&
+          p->workspace == workspace) {
+        plan = p.get();
+        break;
+      }
+    if (!plan) {
+      check_geometry(h, batch, n_cond, height, width);
+      PF_CHECK(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "workspace must be 1024-byte aligned");
+      std::unique_ptr<Plan> np(new Plan());
+      np->B = batch; np->n_cond = n_cond; np->H = height; np->W = width;
+      np->workspace = workspace;
+      Builder b(h, np.get(), static_cast<char*>(workspace), false, batch, n_cond);
+      b.cond_ext = cond;
+      b.build(height, width);
+      np->bytes = b.arena.peak();
+      PF_CHECK(np->bytes <= workspace_bytes, "workspace too small: need %zu bytes, got %zu", np->bytes,
+               workspace_bytes);
+      if (h->plans.size() >= 8) h->plans.erase(h->plans.begin());
+      h->plans.push_back(std::move(np));
+      plan = h->plans.back().get();
+    }
+    PF_CHECK(plan->bytes <= workspace_bytes, "workspace too small");
+    h->last_plan = plan;
+    run_plan(h, *plan, x, time_steps, cond, out, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int32_t pf_unet_launch_count(pf_unet* h) {
+  return h && h->last_plan ? static_cast<int32_t>(h->last_plan->ops.size()) : 0;
+}
+
+static StepArgs to_step(const pf_step_args* a) {
+  StepArgs s;
+  s.x = a->x; s.e_cond = a->e_cond; s.e_uncond = a->e_uncond; s.noise = a->noise;
+  s.orig = a->orig; s.mask = a->mask; s.noise_kn = a->noise_kn;
+  s.x_prev = a->x_prev; s.x0 = a->x0; s.e_t = a->e_t;
+  s.n = a->n; s.noise_bcast = a->noise_bcast; s.uncond_scale = a->uncond_scale;
+  s.c0 = a->c0; s.c1 = a->c1; s.c2 = a->c2; s.c3 = a->c3; s.c4 = a->c4;
+  s.temperature = a->temperature; s.kn_a = a->kn_a; s.kn_b = a->kn_b;
+  return s;
+}
+
+int pf_sample_step_ddpm(const pf_step_args* a, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(a && a->x && a->e_cond && a->x_prev && a->n > 0, "bad step arguments");
+    PF_CHECK(!a->orig || a->mask, "RePaint needs a mask (sampler_sdf.py:310)");
+    launch_step_ddpm(to_step(a), static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+int pf_sample_step_ddim(const pf_step_args* a, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(a && a->x && a->e_cond && a->x_prev && a->n > 0, "bad step arguments");
+    PF_CHECK(!a->orig || a->mask, "RePaint needs a mask");
+    launch_step_ddim(to_step(a), static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+int pf_sample_step_ddpm_legacy(const pf_step_args* a, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(a && a->x && a->e_cond && a->x_prev && a->n > 0, "bad step arguments");
+    launch_step_ddpm_legacy(to_step(a), static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+int pf_q_sample(const float* x0, const float* noise, float* out, int64_t n, float a, float b,
+                pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(x0 && noise && out && n > 0, "bad q_sample arguments");
+    launch_q_sample(x0, noise, out, n, a, b, static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
+}  // extern "C"
+
+// =================================================================================== test ops
+// Building blocks exposed for the parity tests.  They reuse the plan Builder on a throw-away model,
+// allocate their own scratch and synchronise; they are not on the sampling path.
+namespace pf {
+
+struct TempModel {
+  pf_unet m;
+  void* ws = nullptr;
+  TempModel() {
+    memset(&m.cfg, 0, sizeof m.cfg);
+    int dev = 0;
+    PF_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    PF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    PF_CHECK(prop.major == 10, "this library targets sm_100a (B200); found sm_%d%d", prop.major, prop.minor);
+    m.num_sms = prop.multiProcessorCount;
+    PF_CUDA(gemm_init_attrs());
+    m.packing = true;
+  }
+  ~TempModel() {
+    for (void* p : m.owned) cudaFree(p);
+    if (ws) cudaFree(ws);
+  }
+  void set(const char* name, const float* p, std::vector<int64_t> shape) {
+    RawTensor r;
+    r.ptr = p;
+    r.shape = std::move(shape);
+    m.raw[name] = r;
+  }
+};
+
+}  // namespace pf
+
+extern "C" {
+
+int pf_op_conv2d_nhwc(const float* x, int32_t B, int32_t H, int32_t W_, int32_t Cin, const float* w,
+                      int32_t Cout, int32_t ksize, int32_t stride, int32_t upsample,
+                      const float* bias, const float* resid, float* out, int32_t force_bn,
+                      pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(x && w && out, "null argument");
+    PF_CHECK(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
+    PF_CHECK(stride == 1 || (stride == 2 && ksize == 3 && !upsample), "unsupported stride");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TempModel tm;
+    tm.m.pack_stream = s;
+    tm.set("w", w, {Cout, Cin, ksize, ksize});
+    const size_t ws_bytes = static_cast<size_t>(B) * H * W_ * Cin * 2 * 2 * (upsample ? 4 : 1) + (1 << 20);
+    PF_CUDA(cudaMalloc(&tm.ws, ws_bytes));
+    Plan plan;
+    Builder b(&tm.m, &plan, static_cast<char*>(tm.ws), false, B, 1);
+    T xt;
+    xt.p = const_cast<float*>(x); xt.C = Cin; xt.H = H; xt.W = W_;
+    const int layout = upsample ? XF_UP2 : (stride == 2 ? XF_S2D : XF_SAME);
+    Split a = b.act_split(xt, nullptr, nullptr, nullptr, false, layout);
+    const int Ho = upsample ? 2 * H : H / stride, Wo = upsample ? 2 * W_ : W_ / stride;
+    Builder::ASrc src{a, Cin, Wo, Ho, stride == 2 ? 4 * B : B, ksize == 1 ? 0 : (stride == 2 ? 2 : 1)};
+    PackedW& pw = W(&tm.m, "w", {"w"});
+    Op& op = b.conv_gemm(src, pw, nullptr, nullptr, Ho, Wo, Cout);
+    if (force_bn) {
+      PF_CHECK(Cout % force_bn == 0, "force_bn does not divide Cout");
+      op.bn = force_bn;
+      op.g.n_tiles = Cout / force_bn;
+      op.g.nstages = gemm_default_stages(force_bn);
+      auto& mp = wmaps(pw, force_bn, false);
+      op.g.seg[0].b_hi = mp.first;
+      op.g.seg[0].b_lo = mp.second;
+    }
+    b.out_f32(op, out, Cout, bias, 0, resid, Cout);
+    run_plan(&tm.m, plan, nullptr, nullptr, nullptr, nullptr, s);
+    PF_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int pf_op_attention(const float* q, const float* k, const float* v, int32_t B, int32_t N, int32_t Nk,
+                    int32_t heads, float* out, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(q && k && v && out, "null argument");
+    PF_CHECK(N % 128 == 0, "N must be a multiple of 128");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int C = heads * 64;
+    TempModel tm;
+    tm.m.pack_stream = s;
+    const size_t ws_bytes = static_cast<size_t>(B) * heads * N * Nk * 8 +
+                            static_cast<size_t>(B) * (2 * N + 2 * Nk) * C * 4 + (4 << 20);
+    PF_CUDA(cudaMalloc(&tm.ws, ws_bytes));
+    Plan plan;
+    Builder b(&tm.m, &plan, static_cast<char*>(tm.ws), false, B, 1);
+    T qt, kt;
+    qt.p = const_cast<float*>(q); qt.C = C; qt.H = 1; qt.W = N;
+    kt.p = const_cast<float*>(k); kt.C = C; kt.H = 1; kt.W = Nk;
+    Split qs = b.act_split(qt, nullptr, nullptr, nullptr, false, XF_SAME);
+    Split ks = b.act_split(kt, nullptr, nullptr, nullptr, false, XF_SAME);
+    Split vt = b.alloc_split(static_cast<size_t>(B) * Nk * C);
+    Split o = b.alloc_split(static_cast<size_t>(B) * N * C);
+    run_plan(&tm.m, plan, nullptr, nullptr, nullptr, nullptr, s);
+    plan.ops.clear();
+    launch_transpose_split(v, vt.hi, vt.lo, B, Nk, C, s);
+    b.attention_core(qs, C, 0, ks, C, 0, vt, N, N < 128 ? N : 128, N < 128 ? 1 : N / 128, Nk, heads, o, C);
+    run_plan(&tm.m, plan, nullptr, nullptr, nullptr, nullptr, s);
+    launch_merge_split(o.hi, o.lo, out, static_cast<long long>(B) * N * C, s);
+    PF_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int pf_op_groupnorm_nhwc(const float* x, int32_t B, int32_t HW, int32_t C, const float* gamma,
+                         const float* beta, float eps, int32_t silu, float* out, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(x && gamma && beta && out, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TempModel tm;
+    tm.m.pack_stream = s;
+    tm.set("g", gamma, {C});
+    tm.set("b", beta, {C});
+    const size_t ws_bytes = static_cast<size_t>(B) * HW * C * 4 + static_cast<size_t>(B) * C * 32 + (1 << 20);
+    PF_CUDA(cudaMalloc(&tm.ws, ws_bytes));
+    Plan plan;
+    Builder b(&tm.m, &plan, static_cast<char*>(tm.ws), false, B, 1);
+    b.gn_pool_doubles = static_cast<size_t>(B) * C * 2;
+    b.gn_pool = b.alloc<double>(b.gn_pool_doubles);
+    PF_CUDA(cudaMemsetAsync(b.gn_pool, 0, b.gn_pool_doubles * sizeof(double), s));
+    T xt;
+    xt.p = const_cast<float*>(x); xt.C = C; xt.H = 1; xt.W = HW;
+    float *sc, *sh;
+    b.gn_scale_shift(xt, nullptr, "g", "b", eps, sc, sh);
+    Split a = b.act_split(xt, nullptr, sc, sh, silu != 0, XF_SAME);
+    run_plan(&tm.m, plan, nullptr, nullptr, nullptr, nullptr, s);
+    launch_merge_split(a.hi, a.lo, out, static_cast<long long>(B) * HW * C, s);
+    PF_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+}  // extern "C"
