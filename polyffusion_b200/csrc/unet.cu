@@ -677,6 +677,8 @@ struct Builder {
       if (m->packing || n_cond != 1) {
         F(m, tb + ".attn1.to_out.0.bias");
         F(m, tb + ".attn2.to_out.0.bias");
+        F(m, tb + ".norm2.weight");
+        F(m, tb + ".norm2.bias");
         W(m, tb + ".attn2.to_q.weight", {tb + ".attn2.to_q.weight"});
         if (c.d_cond % 64 == 0) {
           W(m, tb + ".attn2.to_k.weight", {tb + ".attn2.to_k.weight"});

@@ -1,0 +1,131 @@
+"""Host-side owner of one ``pf_unet`` handle (include/pf_b200.h) for a ``UNetModel`` on one GPU.
+
+Lifetime: created lazily on the first CUDA forward; weights are pushed through
+``pf_unet_set_weight`` / ``pf_unet_finalize`` (the library keeps its own packed split-bf16 copy) and
+re-pushed whenever a parameter's storage or version counter changes (``load_state_dict``, ``.to()``,
+optimizer steps).  Workspaces are cached per (batch, n_cond, H, W).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Tuple
+
+import torch
+
+from ._lib import PfError, UNetCfg, check, current_stream, lib, ptr
+
+
+class UNetEngine:
+    def __init__(self, module: "torch.nn.Module", cfg: dict):
+        self.module = module
+        self.cfg = cfg
+        self.handle = ctypes.c_void_p()
+        self.device = None
+        self._stamp = None
+        self._workspaces: Dict[Tuple[int, int, int, int], torch.Tensor] = {}
+        self._keep = []
+
+    # ------------------------------------------------------------------ handle management
+    def _create(self, device: torch.device) -> None:
+        c = UNetCfg()
+        c.in_channels = self.cfg["in_channels"]
+        c.out_channels = self.cfg["out_channels"]
+        c.channels = self.cfg["channels"]
+        c.n_res_blocks = self.cfg["n_res_blocks"]
+        mult = list(self.cfg["channel_multipliers"])
+        if len(mult) > 8:
+            raise PfError("at most 8 resolution levels are supported")
+        c.n_levels = len(mult)
+        for i, m in enumerate(mult):
+            c.channel_multipliers[i] = int(m)
+            c.attention_levels[i] = int(i in set(self.cfg["attention_levels"]))
+        c.n_heads = self.cfg["n_heads"]
+        c.tf_layers = self.cfg["tf_layers"]
+        c.d_cond = self.cfg["d_cond"]
+        with torch.cuda.device(device):
+            check(lib().pf_unet_create(ctypes.byref(c), ctypes.byref(self.handle)))
+        self.device = device
+
+    def _params_stamp(self):
+        return tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+
+    def sync_weights(self, device: torch.device, force: bool = False) -> None:
+        """(Re)pack the module's current parameters into the library."""
+        if self.handle.value is None or self.device != device:
+            self.close()
+            self._create(device)
+            force = True
+        stamp = self._params_stamp()
+        if not force and stamp == self._stamp:
+            return
+        keep = []
+        with torch.cuda.device(device):
+            for name, p in self.module.state_dict().items():
+                t = p.detach().to(device=device, dtype=torch.float32).contiguous()
+                keep.append(t)
+                shape = (ctypes.c_int64 * t.dim())(*t.shape)
+                check(lib().pf_unet_set_weight(self.handle, name.encode(), ptr(t), shape, t.dim()))
+            # frequency table of the sinusoidal timestep embedding, evaluated exactly as
+            # stable_diffusion/model/unet.py:158-164 does (fp32 torch ops on the host)
+            half = self.cfg["channels"] // 2
+            freqs = torch.exp(
+                -math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half
+            ).to(device)
+            keep.append(freqs)
+            shape = (ctypes.c_int64 * 1)(half)
+            check(lib().pf_unet_set_weight(self.handle, b"__time_freqs", ptr(freqs), shape, 1))
+            check(lib().pf_unet_finalize(self.handle, current_stream()))
+        del keep
+        self._stamp = stamp
+        self._workspaces.clear()
+
+    def close(self) -> None:
+        if self.handle.value is not None:
+            lib().pf_unet_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+        self._workspaces.clear()
+        self._stamp = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, t: torch.Tensor, cond: torch.Tensor, out=None) -> torch.Tensor:
+        if not x.is_cuda:
+            raise PfError("polyffusion_b200.UNetModel runs on CUDA tensors only (no CPU fallback)")
+        dev = x.device
+        self.sync_weights(dev)
+        B, Cin, H, W = x.shape
+        if Cin != self.cfg["in_channels"]:
+            raise PfError(f"expected {self.cfg['in_channels']} input channels, got {Cin}")
+        if cond.dim() != 3 or cond.shape[0] != B or cond.shape[2] != self.cfg["d_cond"]:
+            raise PfError(f"cond must be [B, n_cond, {self.cfg['d_cond']}], got {tuple(cond.shape)}")
+        if t.shape != (B,):
+            raise PfError(f"time_steps must be [B], got {tuple(t.shape)}")
+        n_cond = cond.shape[1]
+        x = x.contiguous().float()
+        cond = cond.to(dev).contiguous().float()
+        t = t.to(device=dev, dtype=torch.int64).contiguous()
+        key = (B, n_cond, H, W)
+        with torch.cuda.device(dev):
+            ws = self._workspaces.get(key)
+            if ws is None:
+                nbytes = lib().pf_unet_workspace_bytes(self.handle, B, n_cond, H, W)
+                if nbytes == 0:
+                    raise PfError(lib().pf_last_error().decode("utf-8", "replace"))
+                ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+                self._workspaces[key] = ws
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            if out is None:
+                out = torch.empty((B, self.cfg["out_channels"], H, W), dtype=torch.float32, device=dev)
+            check(lib().pf_unet_forward(self.handle, ptr(x), ptr(t), ptr(cond), B, n_cond, H, W, ptr(out),
+                                        ctypes.c_void_p(base), ws.numel() - (base - ws.data_ptr()),
+                                        current_stream()))
+        return out
+
+    def launch_count(self) -> int:
+        return int(lib().pf_unet_launch_count(self.handle)) if self.handle.value is not None else 0
