@@ -68,6 +68,17 @@ size_t pf_unet_workspace_bytes(pf_unet* h, int32_t batch, int32_t n_cond, int32_
 int pf_unet_forward(pf_unet* h, const float* x, const int64_t* time_steps, const float* cond,
                     int32_t batch, int32_t n_cond, int32_t height, int32_t width, float* out,
                     void* workspace, size_t workspace_bytes, pf_stream stream);
+/* Same as pf_unet_forward but brackets every kernel of the plan with CUDA events on `stream`,
+ * synchronises, and reports per-launch milliseconds, algorithmic FLOPs (2*M*N*K for the tcgen05
+ * GEMM launches, 0 otherwise) and the op kind (0 = tcgen05 GEMM, 1 = first conv, 2/3 = GroupNorm
+ * statistics / finalize, 4 = operand transform, 5 = LayerNorm, 6 = GeGLU, 7 = softmax, 8 = timestep
+ * sinusoid, 9 = small linear, 10 = final conv, 11 = memset) into host arrays.  Measurement aid for
+ * bench.py's roofline; not used on the sampling path. */
+int pf_unet_forward_profiled(pf_unet* h, const float* x, const int64_t* time_steps,
+                             const float* cond, int32_t batch, int32_t n_cond, int32_t height,
+                             int32_t width, float* out, void* workspace, size_t workspace_bytes,
+                             pf_stream stream, float* op_ms_host, double* op_flops_host,
+                             int32_t* op_kind_host, int32_t max_ops, int32_t* n_ops);
 /* number of kernel launches one pf_unet_forward issues for the last-used plan */
 int32_t pf_unet_launch_count(pf_unet* h);
 

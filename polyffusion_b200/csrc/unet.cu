@@ -971,8 +971,10 @@ struct Builder {
 
 // =================================================================================== execution
 static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, const float* cond,
-                     float* out, cudaStream_t s) {
+                     float* out, cudaStream_t s, std::vector<cudaEvent_t>* events = nullptr) {
+  size_t opi = 0;
   for (Op& op : plan.ops) {
+    if (events) PF_CUDA(cudaEventRecord((*events)[opi++], s));
     switch (op.kind) {
       case OP_MEMSET:
         PF_CUDA(cudaMemsetAsync(op.o[0], 0, static_cast<size_t>(op.i[0]), s));
@@ -1033,7 +1035,16 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
         break;
     }
   }
+  if (events) PF_CUDA(cudaEventRecord((*events)[opi], s));
   PF_CUDA(cudaGetLastError());
+}
+
+// algorithmic FLOPs (2*M*N*K, single product: the 3x split is an implementation cost) of a GEMM op
+static double gemm_flops(const Op& op) {
+  const GemmParams& g = op.g;
+  double k = 0;
+  for (int s = 0; s < g.nseg; ++s) k += static_cast<double>(g.seg[s].ntaps) * g.seg[s].kb_per_tap * 64;
+  return 2.0 * (static_cast<double>(g.m_tiles) * 128 * g.z_count) * (static_cast<double>(g.n_tiles) * op.bn) * k;
 }
 
 static void check_geometry(pf_unet* m, int B, int n_cond, int H, int Wd) {
@@ -1141,12 +1152,50 @@ size_t pf_unet_workspace_bytes(pf_unet* h, int32_t batch, int32_t n_cond, int32_
   return rc == 0 ? bytes : 0;
 }
 
+static Plan* get_plan(pf_unet* h, const float* cond, int32_t batch, int32_t n_cond, int32_t height,
+                      int32_t width, void* workspace, size_t workspace_bytes);
+
 int pf_unet_forward(pf_unet* h, const float* x, const int64_t* time_steps, const float* cond,
                     int32_t batch, int32_t n_cond, int32_t height, int32_t width, float* out,
                     void* workspace, size_t workspace_bytes, pf_stream stream) {
   return guarded([&] {
     PF_CHECK(h && h->finalized, "model not finalized");
     PF_CHECK(x && time_steps && cond && out && workspace, "null argument");
+    Plan* plan = get_plan(h, cond, batch, n_cond, height, width, workspace, workspace_bytes);
+    run_plan(h, *plan, x, time_steps, cond, out, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int pf_unet_forward_profiled(pf_unet* h, const float* x, const int64_t* time_steps, const float* cond,
+                             int32_t batch, int32_t n_cond, int32_t height, int32_t width, float* out,
+                             void* workspace, size_t workspace_bytes, pf_stream stream,
+                             float* op_ms_host, double* op_flops_host, int32_t* op_kind_host,
+                             int32_t max_ops, int32_t* n_ops) {
+  return guarded([&] {
+    PF_CHECK(h && h->finalized, "model not finalized");
+    PF_CHECK(x && time_steps && cond && out && workspace && op_ms_host && op_flops_host &&
+                 op_kind_host && n_ops, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Plan* plan = get_plan(h, cond, batch, n_cond, height, width, workspace, workspace_bytes);
+    const size_t n = plan->ops.size();
+    PF_CHECK(static_cast<size_t>(max_ops) >= n, "profile buffers too small: need %zu ops", n);
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) PF_CUDA(cudaEventCreate(&e));
+    run_plan(h, *plan, x, time_steps, cond, out, s, &ev);
+    PF_CUDA(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < n; ++i) {
+      PF_CUDA(cudaEventElapsedTime(&op_ms_host[i], ev[i], ev[i + 1]));
+      op_kind_host[i] = static_cast<int32_t>(plan->ops[i].kind);
+      op_flops_host[i] = plan->ops[i].kind == OP_GEMM ? gemm_flops(plan->ops[i]) : 0.0;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    *n_ops = static_cast<int32_t>(n);
+  });
+}
+
+static Plan* get_plan(pf_unet* h, const float* cond, int32_t batch, int32_t n_cond, int32_t height,
+                      int32_t width, void* workspace, size_t workspace_bytes) {
+  {
     Plan* plan = nullptr;
     for (auto& p : h->plans)
       if (p->B == batch && p->n_cond == n_cond && p->H == height && p->W == width &&
@@ -1172,8 +1221,8 @@ int pf_unet_forward(pf_unet* h, const float* x, const int64_t* time_steps, const
     }
     PF_CHECK(plan->bytes <= workspace_bytes, "workspace too small");
     h->last_plan = plan;
-    run_plan(h, *plan, x, time_steps, cond, out, static_cast<cudaStream_t>(stream));
-  });
+    return plan;
+  }
 }
 
 int32_t pf_unet_launch_count(pf_unet* h) {

@@ -94,7 +94,9 @@ class UNetEngine:
             pass
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, t: torch.Tensor, cond: torch.Tensor, out=None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, t: torch.Tensor, cond: torch.Tensor, out=None, profile=None) -> torch.Tensor:
+        """``profile``: optional dict; when given, the plan runs once with CUDA events around every
+        launch and the dict receives ``ms`` / ``flops`` / ``kind`` lists (pf_unet_forward_profiled)."""
         if not x.is_cuda:
             raise PfError("polyffusion_b200.UNetModel runs on CUDA tensors only (no CPU fallback)")
         dev = x.device
@@ -122,9 +124,24 @@ class UNetEngine:
             base = (ws.data_ptr() + 1023) // 1024 * 1024
             if out is None:
                 out = torch.empty((B, self.cfg["out_channels"], H, W), dtype=torch.float32, device=dev)
-            check(lib().pf_unet_forward(self.handle, ptr(x), ptr(t), ptr(cond), B, n_cond, H, W, ptr(out),
-                                        ctypes.c_void_p(base), ws.numel() - (base - ws.data_ptr()),
-                                        current_stream()))
+            if profile is None:
+                check(lib().pf_unet_forward(self.handle, ptr(x), ptr(t), ptr(cond), B, n_cond, H, W,
+                                            ptr(out), ctypes.c_void_p(base),
+                                            ws.numel() - (base - ws.data_ptr()), current_stream()))
+            else:
+                cap = 4096
+                ms = (ctypes.c_float * cap)()
+                fl = (ctypes.c_double * cap)()
+                kd = (ctypes.c_int32 * cap)()
+                n = ctypes.c_int32(0)
+                check(lib().pf_unet_forward_profiled(
+                    self.handle, ptr(x), ptr(t), ptr(cond), B, n_cond, H, W, ptr(out),
+                    ctypes.c_void_p(base), ws.numel() - (base - ws.data_ptr()), current_stream(),
+                    ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(fl, ctypes.c_void_p),
+                    ctypes.cast(kd, ctypes.c_void_p), cap, ctypes.cast(ctypes.byref(n), ctypes.c_void_p)))
+                profile["ms"] = list(ms[: n.value])
+                profile["flops"] = list(fl[: n.value])
+                profile["kind"] = list(kd[: n.value])
         return out
 
     def launch_count(self) -> int:
