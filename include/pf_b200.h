@@ -79,6 +79,8 @@ int pf_unet_forward_profiled(pf_unet* h, const float* x, const int64_t* time_ste
                              int32_t width, float* out, void* workspace, size_t workspace_bytes,
                              pf_stream stream, float* op_ms_host, double* op_flops_host,
                              int32_t* op_kind_host, int32_t max_ops, int32_t* n_ops);
+/* human-readable description of launch i of the last-used plan (measurement aid) */
+int pf_unet_op_desc(pf_unet* h, int32_t i, char* buf, int32_t len);
 /* number of kernel launches one pf_unet_forward issues for the last-used plan */
 int32_t pf_unet_launch_count(pf_unet* h);
 

@@ -7,3 +7,28 @@ Drop-in module surface (same import paths below this package as below the refere
 All arithmetic runs in hand-written CUDA kernels behind the C ABI in ``include/pf_b200.h``.
 """
 __version__ = "0.1.0"
+
+
+_DROPIN_MODULES = {
+    "stable_diffusion": "polyffusion_b200.stable_diffusion",
+    "stable_diffusion.model": "polyffusion_b200.stable_diffusion.model",
+    "stable_diffusion.model.unet": "polyffusion_b200.stable_diffusion.model.unet",
+    "stable_diffusion.model.unet_attention": "polyffusion_b200.stable_diffusion.model.unet_attention",
+    "stable_diffusion.latent_diffusion": "polyffusion_b200.stable_diffusion.latent_diffusion",
+    "stable_diffusion.sampler": "polyffusion_b200.stable_diffusion.sampler",
+    "sampler_sdf": "polyffusion_b200.sampler_sdf",
+    "sampler_ddim": "polyffusion_b200.sampler_ddim",
+    "ddpm": "polyffusion_b200.ddpm",
+}
+
+
+def install_dropin() -> None:
+    """Alias the reference's top-level module names (``stable_diffusion.model.unet``, ``sampler_sdf``,
+    ``sampler_ddim``, ``ddpm`` ...) to this package in ``sys.modules``, so that the reference's own
+    ``inference_sdf.py`` / ``models/model_sdf.py`` imports resolve to the CUDA implementation.
+    Call it before importing the reference scripts."""
+    import importlib
+    import sys
+
+    for alias, target in _DROPIN_MODULES.items():
+        sys.modules[alias] = importlib.import_module(target)

@@ -78,6 +78,7 @@ SYMBOLS = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
          c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p],
     ),
+    "pf_unet_op_desc": (c_int32, [c_void_p, c_int32, c_char_p, c_int32]),
     "pf_unet_launch_count": (c_int32, [c_void_p]),
     "pf_sample_step_ddpm": (c_int32, [POINTER(StepArgs), c_void_p]),
     "pf_sample_step_ddim": (c_int32, [POINTER(StepArgs), c_void_p]),

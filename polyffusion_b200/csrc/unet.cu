@@ -1225,6 +1225,27 @@ static Plan* get_plan(pf_unet* h, const float* cond, int32_t batch, int32_t n_co
   }
 }
 
+int pf_unet_op_desc(pf_unet* h, int32_t i, char* buf, int32_t len) {
+  return guarded([&] {
+    PF_CHECK(h && h->last_plan && buf && len > 0, "no plan");
+    PF_CHECK(i >= 0 && static_cast<size_t>(i) < h->last_plan->ops.size(), "op index out of range");
+    const Op& op = h->last_plan->ops[i];
+    static const char* names[] = {"gemm", "conv_in", "gn_stats", "gn_finalize", "act_split", "ln_split",
+                                  "geglu", "softmax", "time_sin", "small_linear", "conv_out", "memset"};
+    if (op.kind == OP_GEMM) {
+      const GemmParams& g = op.g;
+      int k = 0;
+      for (int s = 0; s < g.nseg; ++s) k += g.seg[s].ntaps * g.seg[s].kb_per_tap * 64;
+      snprintf(buf, len, "gemm M=%lld N=%d K=%d bn=%d taps=%d nseg=%d z=%d mode=%d stages=%d",
+               static_cast<long long>(g.m_tiles) * 128, g.n_tiles * op.bn, k, op.bn, g.seg[0].ntaps,
+               g.nseg, g.z_count, g.mode, g.nstages);
+    } else {
+      snprintf(buf, len, "%s i=[%lld,%lld,%lld,%lld,%lld,%lld,%lld]", names[op.kind], op.i[0], op.i[1],
+               op.i[2], op.i[3], op.i[4], op.i[5], op.i[6]);
+    }
+  });
+}
+
 int32_t pf_unet_launch_count(pf_unet* h) {
   return h && h->last_plan ? static_cast<int32_t>(h->last_plan->ops.size()) : 0;
 }

@@ -144,5 +144,13 @@ class UNetEngine:
                 profile["kind"] = list(kd[: n.value])
         return out
 
+    def op_descriptions(self):
+        out = []
+        buf = ctypes.create_string_buffer(256)
+        for i in range(self.launch_count()):
+            check(lib().pf_unet_op_desc(self.handle, i, buf, 256))
+            out.append(buf.value.decode())
+        return out
+
     def launch_count(self) -> int:
         return int(lib().pf_unet_launch_count(self.handle)) if self.handle.value is not None else 0

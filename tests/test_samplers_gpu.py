@@ -1,0 +1,200 @@
+"""GPU: the CUDA samplers (UNet plan + fused step kernels, through the C ABI) against the CPU oracle
+and against the golden outputs of the real reference, with the SAME injected noise on both sides.
+
+Tolerances: a reverse step maps an eps error e to about sqrt(1/alpha_bar - 1) * mean_x0_coef * e in
+x_{t-1}; near t = 0 .. 3 and t = 997 .. 999 that factor is <= 1, so short chains stay within the UNet
+tolerance (rtol 1e-3 / atol 1e-4).  The step kernels alone are compared at 1e-6 (they round every fp32
+op exactly like the reference's ATen ops; only the device's pow/exp in the tables may differ by an ulp).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _util import ATOL, RTOL, NoiseTape, build_unet, close_report, oracle_cfg
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in np.load(os.path.join(GOLD, name)).items()}
+
+
+class CudaTape:
+    """Monkeypatch torch.randn / randn_like so the CUDA samplers draw from a CPU-seeded tape."""
+
+    def __init__(self, seed):
+        self.tape = NoiseTape(seed)
+        self._randn, self._randn_like = torch.randn, torch.randn_like
+
+    def __enter__(self):
+        def randn(*size, **kw):
+            if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)):
+                size = tuple(size[0])
+            return self.tape(size).cuda()
+
+        torch.randn = randn
+        torch.randn_like = lambda t, **kw: self.tape(t.shape).cuda()
+        return self
+
+    def __exit__(self, *a):
+        torch.randn, torch.randn_like = self._randn, self._randn_like
+
+
+@pytest.fixture(scope="module")
+def rig():
+    from polyffusion_b200.stable_diffusion.latent_diffusion import LatentDiffusion
+
+    unet = build_unet(512)
+    sd = {k: v.clone() for k, v in unet.state_dict().items()}
+    ldm = LatentDiffusion(unet, None, 0.18215, 1000, 0.00085, 0.012).cuda()
+    from oracle.unet_oracle import unet_forward
+
+    eps_fn = lambda x, t, c: unet_forward(sd, oracle_cfg(512), x, t, c)
+    return ldm, eps_fn
+
+
+def _assert_close(out, ref, what):
+    err, frac = close_report(out, ref)
+    print(f"{what}: max abs err {err:.3e}, within tol {frac:.6f}")
+    assert frac == 1.0, f"{what}: max abs err {err}, fraction within rtol {RTOL}/atol {ATOL} = {frac}"
+
+
+def test_step_kernels_match_oracle_arithmetic(rig):
+    """Given the SAME eps, the fused DDPM / DDIM step kernels reproduce the reference arithmetic."""
+    from oracle import sampler_oracle as so
+    from polyffusion_b200.sampler_ddim import DDIMSampler
+    from polyffusion_b200.sampler_sdf import SDFSampler
+
+    ldm, _ = rig
+    g = torch.Generator().manual_seed(4)
+    x, e_c, e_u, nz, orig, nk = (torch.randn(2, 2, 128, 128, generator=g) for _ in range(6))
+    mask = (torch.rand(2, 2, 128, 128, generator=g) < 0.4).float()
+    _, beta, alpha_bar = so.ldm_schedule()
+    tb = so.ddpm_tables(alpha_bar, beta)
+    s = SDFSampler(ldm)
+    from polyffusion_b200._step import fused_step
+
+    for step in (999, 500, 1, 0):
+        eps = e_u + 3.0 * (e_c - e_u)
+        want, want_x0, _ = so.ddpm_p_sample(tb, lambda *_: eps, x, None, step, lambda shape: nz)
+        x_kn = tb["sqrt_ab"][step] * orig + tb["sqrt_1m_ab"][step] * (nk if step > 0 else 0 * nk)
+        want = x_kn * mask + want * (1 - mask)
+        got, got_x0, got_e = fused_step(
+            "ddpm", x.cuda(), e_c.cuda(), e_u.cuda(), nz.cuda() if step > 0 else None, s._coefs(step),
+            uncond_scale=3.0, orig=orig.cuda(), mask=mask.cuda(), noise_kn=nk.cuda() if step > 0 else None,
+            kn=(s._h["qa"][step], s._h["qb"][step]))
+        assert (got.cpu() - want).abs().max().item() < 2e-6 * max(1.0, want.abs().max().item())
+        assert (got_x0.cpu() - want_x0).abs().max().item() < 2e-6 * max(1.0, want_x0.abs().max().item())
+        assert (got_e.cpu() - eps).abs().max().item() < 1e-6
+    d = DDIMSampler(ldm, 50, "uniform", 0.7)
+    tbd = so.ddim_tables(alpha_bar, so.ddim_time_steps(1000, 50), 0.7)
+    for index in (49, 20, 0):
+        want, want_x0 = so.ddim_step(tbd, e_c, index, x, lambda shape: nz)
+        with CudaTape(0) as ct:
+            ct.tape = lambda shape: nz
+            got, got_x0 = d.get_x_prev_and_pred_x0(e_c.cuda(), index, x.cuda(), temperature=1.0, repeat_noise=False)
+        assert (got.cpu() - want).abs().max().item() < 2e-6 * max(1.0, want.abs().max().item())
+        assert (got_x0.cpu() - want_x0).abs().max().item() < 2e-6 * max(1.0, want_x0.abs().max().item())
+
+
+def test_ddpm_paint_cfg_vs_oracle_and_golden(rig):
+    from oracle import sampler_oracle as so
+    from polyffusion_b200.sampler_sdf import SDFSampler
+
+    ldm, eps_fn = rig
+    g = load("paint_ddpm_cfg5.npz")
+    s = SDFSampler(ldm)
+    with CudaTape(int(g["tape_seed"])):
+        xt = s.q_sample(g["orig"].cuda(), 2, torch.randn(1, 2, 128, 128))
+        out = s.paint(xt, g["cond"].cuda(), 2, orig=g["orig"].cuda(), mask=g["mask"].cuda(),
+                      uncond_scale=5.0, uncond_cond=g["uncond"].cuda())
+    _assert_close(xt, g["x_t"], "q_sample vs reference golden")
+    _assert_close(out, g["out"], "DDPM paint (CFG 5, RePaint) vs reference golden")
+
+
+def test_ddpm_repaint2_and_sample_vs_golden(rig):
+    from polyffusion_b200.sampler_sdf import SDFSampler
+
+    ldm, _ = rig
+    s = SDFSampler(ldm)
+    g = load("paint_ddpm_repaint2.npz")
+    with CudaTape(int(g["tape_seed"])):
+        out = s.paint(g["x_start"].cuda(), g["cond"].cuda(), 1, orig=g["orig"].cuda(), mask=g["mask"].cuda(),
+                      repaint_n=2)
+    _assert_close(out, g["out"], "DDPM paint repaint_n=2 vs reference golden")
+    g = load("sample_ddpm.npz")
+    with CudaTape(int(g["tape_seed"])):
+        out = s.sample([1, 2, 128, 128], g["cond"].cuda(), x_last=g["x_start"].cuda(), t_start=int(g["t_start"]))
+    _assert_close(out, g["out"], "DDPM sample vs reference golden")
+
+
+def test_ddim_vs_golden(rig):
+    from polyffusion_b200.sampler_ddim import DDIMSampler
+
+    ldm, _ = rig
+    g = load("ddim.npz")
+    d = DDIMSampler(ldm, 4, "uniform", 0.0)
+    with CudaTape(int(g["sample_tape_seed"])):
+        out = d.sample([1, 2, 128, 128], g["cond"].cuda(), x_last=g["x_start"].cuda(), t_start=int(g["sample_t_start"]))
+    _assert_close(out, g["sample_out"], "DDIM sample vs reference golden")
+    d = DDIMSampler(ldm, 4, "uniform", float(g["paint_eta"]))
+    with CudaTape(int(g["paint_tape_seed"])):
+        out = d.paint(g["x_start"].cuda(), g["cond"].cuda(), int(g["paint_t_start"]), orig=g["orig"].cuda(),
+                      mask=g["mask"].cuda(), orig_noise=g["orig_noise"].cuda())
+    _assert_close(out, g["paint_out"], "DDIM paint (eta 1) vs reference golden")
+
+
+def test_ddpm_paint_batch_vs_oracle(rig):
+    """B = 3 (odd batch), plain generation exactly as inference_sdf.py:218-220,289-301 runs it:
+    orig = mask = 0, q_sample from t_idx then paint."""
+    from oracle import sampler_oracle as so
+    from polyffusion_b200.sampler_sdf import SDFSampler
+
+    ldm, eps_fn = rig
+    g = torch.Generator().manual_seed(6)
+    cond = torch.randn(3, 1, 512, generator=g)
+    x0 = torch.randn(3, 2, 128, 128, generator=g)
+    zeros = torch.zeros(3, 2, 128, 128)
+    _, beta, alpha_bar = so.ldm_schedule()
+    want = so.ddpm_paint(alpha_bar, beta, eps_fn, x0, cond, 2, NoiseTape(8), orig=zeros, mask=zeros)
+    s = SDFSampler(ldm)
+    with CudaTape(8):
+        got = s.paint(x0.cuda(), cond.cuda(), 2, orig=zeros.cuda(), mask=zeros.cuda())
+    _assert_close(got, want, "DDPM paint B=3 vs oracle")
+
+
+def test_legacy_ddpm_vs_golden():
+    """BASELINE config 1 plumbing: DenoiseDiffusion.p_sample, B = 4, 10 reverse steps (999..990)."""
+    from polyffusion_b200.ddpm import DenoiseDiffusion
+
+    g = load("legacy_ddpm.npz")
+
+    class TinyEps(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(7)
+            self.conv = torch.nn.Conv2d(2, 2, 3, padding=1)
+
+        def forward(self, x, t):
+            return self.conv(x) + (t.float() / 1000.0)[:, None, None, None]
+
+    dd = DenoiseDiffusion(TinyEps(), 1000).cuda()
+    x = g["x_T"].cuda()
+    with CudaTape(int(g["tape_seed"])):
+        for ti in range(999, 989, -1):
+            x = dd.p_sample(x, x.new_full((4,), ti, dtype=torch.long))
+    err = (x.cpu() - g["out"]).abs().max().item()
+    print("legacy ddpm 10 steps: max abs err", err)
+    assert err < 1e-4
+
+
+def test_unet_vs_reference_goldens():
+    for name, d_cond in (("unet_chd8bar_b2.npz", 512), ("unet_txtvnl_b1.npz", 128)):
+        g = load(name)
+        m = build_unet(d_cond).cuda()
+        with torch.no_grad():
+            out = m(g["x"].cuda(), g["t"].cuda(), g["cond"].cuda())
+        _assert_close(out, g["eps"], f"UNet vs reference golden {name}")
