@@ -12,6 +12,7 @@
 namespace pf {
 
 constexpr int MAX_STAGES = 8;
+constexpr int STG_PITCH = 36;  // floats per staged row (32 + 4 pad: conflict-free float4 access)
 
 struct TileCoord {
   int n0, tile, zb, zh, img, trem, x0, y0;
@@ -153,8 +154,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else {
     // ------------------------------------------------------------------ epilogue
+    // TMEM -> registers (thread = output row) -> per-warp smem staging -> coalesced global stores:
+    // in the store phase a quarter-warp (8 lanes x float4) covers one 128-byte row segment, so
+    // every store / residual load touches whole 128 B lines.  Optional per-channel sum / sum-of-
+    // squares of the stored values (GroupNorm statistics for the consumer) are reduced in
+    // registers -> shuffles -> smem atomics -> one fp64 atomicAdd per (tile, column).
     const int q = warp & 3;       // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;  // row inside the tile
+    const int ewarp = warp - 2;   // 0..3
+    float* stg = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw)) + nstages * STAGE_BYTES) +
+                 ewarp * (32 * STG_PITCH);
+    float* sacc = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw)) + nstages * STAGE_BYTES) +
+                  4 * 32 * STG_PITCH;  // [2 parity][2][BN]
+    const int et = threadIdx.x - 64;  // 0..127 among epilogue threads
+    if (p.stats) {
+      for (int i = et; i < 4 * BN; i += 128) sacc[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     int lt = 0;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       const TileCoord tc = decode_tile(p, t, BN);
@@ -164,58 +180,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-      const long long m = static_cast<long long>(tc.tile) * GEMM_BM + r;
+      const long long m0 = static_cast<long long>(tc.tile) * GEMM_BM + q * 32;  // first row of this warp
       const long long zoff = tc.zb * p.out_zb + tc.zh * p.out_zh;
+      float* sa = sacc + as * 2 * BN;
 
-      if (p.mode == OUT_F32) {
-        float* orow = p.out + zoff + m * p.ldc + tc.n0;
-        const float* av =
-            p.addvec ? p.addvec + static_cast<long long>(tc.img) * p.addvec_ld + tc.n0 : nullptr;
-        const float* rr = p.resid ? p.resid + m * p.ldr + tc.n0 : nullptr;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o;
-            o.x = __uint_as_float(v[4 * j + 0]);
-            o.y = __uint_as_float(v[4 * j + 1]);
-            o.z = __uint_as_float(v[4 * j + 2]);
-            o.w = __uint_as_float(v[4 * j + 3]);
-            if (av) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(av + c) + j);
-              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-            }
-            if (rr) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(rr + c) + j);
-              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-            }
-            reinterpret_cast<float4*>(orow + c)[j] = o;
-          }
-        }
-      } else if (p.mode == OUT_SPLIT) {
-        __nv_bfloat16* oh = p.out_hi + zoff + m * p.ldc + tc.n0;
-        __nv_bfloat16* ol = p.out_lo + zoff + m * p.ldc + tc.n0;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 h, l;
-            split2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]), h.x, l.x);
-            split2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]), h.y, l.y);
-            split2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]), h.z, l.z);
-            split2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]), h.w, l.w);
-            reinterpret_cast<uint4*>(oh + c)[j] = h;
-            reinterpret_cast<uint4*>(ol + c)[j] = l;
-          }
-        }
-      } else {  // OUT_SPLIT_T: [img][n][token]; consecutive lanes -> consecutive tokens
-        const long long tok = static_cast<long long>(tc.trem) * GEMM_BM + r;
+      if (p.mode == OUT_SPLIT_T) {
+        // [img][n][token]; consecutive lanes -> consecutive tokens (already coalesced)
+        const long long tok = static_cast<long long>(tc.trem) * GEMM_BM + q * 32 + lane;
         const long long base = zoff + static_cast<long long>(tc.img) * p.out_img + tok;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
@@ -231,11 +202,106 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             p.out_lo[o] = l;
           }
         }
+      } else {
+        const bool geglu = (p.mode == OUT_GEGLU);
+        const int ncols = geglu ? BN / 2 : BN;          // output columns produced by this tile
+        const int ocol0 = geglu ? (tc.n0 / 2) : tc.n0;  // first output column
+        const float* av = p.addvec ? p.addvec + static_cast<long long>(tc.img) * p.addvec_ld : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < ncols; c += 32) {
+          {
+            uint32_t v[32];
+            tmem_ld32(taddr + c, v);
+            if (geglu) {
+              uint32_t g[32];
+              tmem_ld32(taddr + BN / 2 + c, g);
+              tmem_ld_wait();
+              // value = cols [ocol0 + c, +32) of the first half, gate = same cols of the second
+              // half of the (un-interleaved) projection: out = (x + b_x) * gelu(g + b_g)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float xv = __uint_as_float(v[j]) + __ldg(av + ocol0 + c + j);
+                const float gv = __uint_as_float(g[j]) + __ldg(av + p.geglu_f + ocol0 + c + j);
+                v[j] = __float_as_uint(xv * (0.5f * gv * (1.0f + erff(gv * 0.70710678118654752440f))));
+              }
+            } else {
+              tmem_ld_wait();
+              if (av) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(av + tc.n0 + c + j));
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + 4 * j) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          __syncwarp();
+          float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + rsub;
+            float4 o = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + c4);
+            const long long m = m0 + row;
+            if (p.mode == OUT_F32) {
+              if (p.resid) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p.resid + m * p.ldr + tc.n0 + c + c4));
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              *reinterpret_cast<float4*>(p.out + zoff + m * p.ldc + tc.n0 + c + c4) = o;
+              ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
+              ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y);
+              ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+            } else {  // OUT_SPLIT / OUT_GEGLU: split-bf16 row-major
+              uint2 h, l;
+              split2(o.x, o.y, h.x, l.x);
+              split2(o.z, o.w, h.y, l.y);
+              const long long off = zoff + m * p.ldc + ocol0 + c + c4;
+              *reinterpret_cast<uint2*>(p.out_hi + off) = h;
+              *reinterpret_cast<uint2*>(p.out_lo + off) = l;
+            }
+          }
+          if (p.stats) {
+            // reduce over the 4 row-groups of the warp (lanes with equal lane&7), then smem atomics
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, o);
+              ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, o);
+              ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, o);
+              ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, o);
+              ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, o);
+              ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, o);
+              ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, o);
+              ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, o);
+            }
+            if (lane < 8) {
+              float* d = sa + c + c4;
+              atomicAdd(d + 0, ssum.x); atomicAdd(d + 1, ssum.y);
+              atomicAdd(d + 2, ssum.z); atomicAdd(d + 3, ssum.w);
+              atomicAdd(d + BN + 0, ssq.x); atomicAdd(d + BN + 1, ssq.y);
+              atomicAdd(d + BN + 2, ssq.z); atomicAdd(d + BN + 3, ssq.w);
+            }
+          }
+          __syncwarp();
+        }
       }
       // all of this warp's TMEM reads for the tile are complete (tmem_ld_wait above)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+      if (p.stats) {
+        // flush this tile's column sums: [img][stats_ld][2] fp64
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int col = et; col < BN; col += 128) {
+          const float s1 = sa[col], s2 = sa[BN + col];
+          sa[col] = 0.f;
+          sa[BN + col] = 0.f;
+          double* d = p.stats + (static_cast<long long>(tc.img) * p.stats_ld + tc.n0 + col) * 2;
+          atomicAdd(d, static_cast<double>(s1));
+          atomicAdd(d + 1, static_cast<double>(s2));
+        }
+      }
     }
   }
 
@@ -249,16 +315,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
 cudaError_t gemm_init_attrs() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   return e;
 }
 
 cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t stream) {
-  const int smem = gemm_smem_bytes(bn, p.nstages);
+  const int smem = gemm_smem_bytes(bn, p.nstages) + gemm_epilogue_smem_bytes(bn);
   const long long total = static_cast<long long>(p.n_tiles) * p.m_tiles * p.z_count;
   const unsigned grid = static_cast<unsigned>(total < num_ctas ? total : num_ctas);
   switch (bn) {

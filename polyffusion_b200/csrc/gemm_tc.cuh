@@ -26,6 +26,7 @@ enum GemmOutMode : int {
   OUT_F32 = 0,        // fp32 row-major [m, ldc] (+ addvec[img, n] + resid[m, n])
   OUT_SPLIT = 1,      // bf16 hi/lo row-major [m, ldc]
   OUT_SPLIT_T = 2,    // bf16 hi/lo transposed per image: [img][n][token]
+  OUT_GEGLU = 3,      // tile = [BN/2 value cols | BN/2 gate cols]: split-bf16 of (x+b)*gelu(g+b)
 };
 
 struct alignas(64) GemmSeg {
@@ -58,11 +59,16 @@ struct alignas(64) GemmParams {
   const float* addvec;  // [img, addvec_ld] or null
   const float* resid;   // [m, ldr] or null
   long long addvec_ld, ldr;
+  double* stats;        // OUT_F32 only: per-(image, column) sum / sum-of-squares [img][stats_ld][2]
+  long long stats_ld;
+  int geglu_f;          // OUT_GEGLU: number of output features F (bias layout [x: F | gate: F])
 };
 
 // smem bytes for a given BN / stage count (incl. 1 KB alignment slack)
 inline int gemm_stage_bytes(int bn) { return 2 * GEMM_BM * 128 + 2 * bn * 128; }
 inline int gemm_smem_bytes(int bn, int nstages) { return nstages * gemm_stage_bytes(bn) + 1024; }
+// epilogue staging (4 warps x 32 rows x 36 floats) + column-statistics accumulators [2][2][bn]
+inline int gemm_epilogue_smem_bytes(int bn) { return 4 * 32 * 36 * 4 + 4 * bn * 4; }
 
 // persistent launch: min(#tiles, num_ctas) CTAs
 cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t stream);

@@ -112,19 +112,25 @@ void launch_gn_stats(const float* src, double* acc, int B, int HW, int Cs, int C
   gn_stats_kernel<<<grid, 256, 0, s>>>(src, acc, HW, Cs, Ctot, coff, ppb);
 }
 
-__global__ void gn_finalize_kernel(const double* __restrict__ acc, const float* __restrict__ gamma,
+__global__ void gn_finalize_kernel(const double* __restrict__ acc0, int C0,
+                                   const double* __restrict__ acc1, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ scale,
                                    float* __restrict__ shift, int HW, int Ctot, int groups,
                                    float eps) {
+  // channel statistics of the (virtually) concatenated tensor: channels [0, C0) come from acc0
+  // [B][C0][2], channels [C0, Ctot) from acc1 [B][Ctot-C0][2]
   const int b = blockIdx.x;
   const int cpg = Ctot / groups;
+  const int C1 = Ctot - C0;
   for (int c = threadIdx.x; c < Ctot; c += blockDim.x) {
     const int g = c / cpg;
     double ts = 0.0, tq = 0.0;
-    const double* a = acc + (static_cast<long long>(b) * Ctot + g * cpg) * 2;
     for (int i = 0; i < cpg; ++i) {
-      ts += a[2 * i];
-      tq += a[2 * i + 1];
+      const int ch = g * cpg + i;
+      const double* a = ch < C0 ? acc0 + (static_cast<long long>(b) * C0 + ch) * 2
+                                : acc1 + (static_cast<long long>(b) * C1 + (ch - C0)) * 2;
+      ts += a[0];
+      tq += a[1];
     }
     const double n = static_cast<double>(HW) * cpg;
     const double mean = ts / n;
@@ -137,9 +143,10 @@ __global__ void gn_finalize_kernel(const double* __restrict__ acc, const float* 
   }
 }
 
-void launch_gn_finalize(const double* acc, const float* gamma, const float* beta, float* scale,
-                        float* shift, int B, int HW, int Ctot, int groups, float eps, cudaStream_t s) {
-  gn_finalize_kernel<<<B, 256, 0, s>>>(acc, gamma, beta, scale, shift, HW, Ctot, groups, eps);
+void launch_gn_finalize(const double* acc0, int C0, const double* acc1, const float* gamma,
+                        const float* beta, float* scale, float* shift, int B, int HW, int Ctot,
+                        int groups, float eps, cudaStream_t s) {
+  gn_finalize_kernel<<<B, 256, 0, s>>>(acc0, C0, acc1, gamma, beta, scale, shift, HW, Ctot, groups, eps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -535,7 +542,7 @@ void launch_conv_out(const float* h, const float* scale, const float* shift, con
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out_hi,
                                    bf16* __restrict__ out_lo, int Cout, int Cin, int taps,
-                                   int cout_total, int row0) {
+                                   int cout_total, int row0, int geglu_gran) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   if (i >= total) return;
@@ -546,15 +553,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
   const float v = w[(static_cast<long long>(co) * Cin + ci) * taps + tap];
   bf16 h, l;
   split_bf16(v, h, l);
-  const long long o = (static_cast<long long>(tap) * cout_total + row0 + co) * Cin + ci;
+  int dst = row0 + co;
+  if (geglu_gran > 0) {
+    // GeGLU projection [x: F rows | gate: F rows] -> tiles of [gran x rows | gran gate rows]
+    const int F = Cout / 2;
+    const int half = co / F, r = co % F;
+    dst = row0 + (r / geglu_gran) * 2 * geglu_gran + half * geglu_gran + r % geglu_gran;
+  }
+  const long long o = (static_cast<long long>(tap) * cout_total + dst) * Cin + ci;
   out_hi[o] = h;
   out_lo[o] = l;
 }
 void launch_pack_weight(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin, int taps,
-                        int cout_total, int row0, cudaStream_t s) {
+                        int cout_total, int row0, int geglu_gran, cudaStream_t s) {
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   pack_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
-      w, out_hi, out_lo, Cout, Cin, taps, cout_total, row0);
+      w, out_hi, out_lo, Cout, Cin, taps, cout_total, row0, geglu_gran);
 }
 
 __global__ void vec_add_kernel(const float* a, const float* b, float* out, int n) {

@@ -17,12 +17,14 @@ void launch_conv_in(const float* x, const float* w, const float* bias, float* ou
                     int H, int W, int Cout, cudaStream_t s);
 
 // per-(sample, channel) sum / sum-of-squares (fp64 atomics) of an NHWC tensor [B,HW,Cs] written at
-// channel offset coff of acc [B, Ctot, 2]
+// channel offset coff of acc [B, Ctot, 2]  (only used for the first conv's output; every other
+// feature map gets its statistics from the producing GEMM's epilogue)
 void launch_gn_stats(const float* src, double* acc, int B, int HW, int Cs, int Ctot, int coff,
                      cudaStream_t s);
 // acc -> scale/shift [B, Ctot] for GroupNorm(groups, eps) with affine gamma/beta
-void launch_gn_finalize(const double* acc, const float* gamma, const float* beta, float* scale,
-                        float* shift, int B, int HW, int Ctot, int groups, float eps, cudaStream_t s);
+void launch_gn_finalize(const double* acc0, int C0, const double* acc1, const float* gamma,
+                        const float* beta, float* scale, float* shift, int B, int HW, int Ctot,
+                        int groups, float eps, cudaStream_t s);
 
 enum XformLayout : int { XF_SAME = 0, XF_UP2 = 1, XF_S2D = 2 };
 // out_hi/lo[b, y', x', c] = split(act(scale*cat(src0,src1) + shift)); act = SiLU if silu.
@@ -58,8 +60,9 @@ void launch_conv_out(const float* h, const float* scale, const float* shift, con
                      cudaStream_t s);
 
 // weight packing: w [Cout, Cin, kh, kw] fp32 -> split bf16 [kh*kw][Cout_total][Cin] rows at row0
+// geglu_gran > 0: interleave the [x | gate] halves of a GeGLU projection in blocks of geglu_gran rows
 void launch_pack_weight(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin, int taps,
-                        int cout_total, int row0, cudaStream_t s);
+                        int cout_total, int row0, int geglu_gran, cudaStream_t s);
 // out[i] = a[i] + b[i] (bias pre-combination); b may be null
 void launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t s);
 

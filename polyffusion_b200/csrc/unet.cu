@@ -255,7 +255,8 @@ static const float* Fcat(pf_unet* m, const std::string& key, const std::vector<s
 }
 
 // split-bf16 tap-major packed GEMM weight: concatenation of `names` along Cout
-static PackedW& W(pf_unet* m, const std::string& key, const std::vector<std::string>& names) {
+static PackedW& W(pf_unet* m, const std::string& key, const std::vector<std::string>& names,
+                  int geglu_gran = 0) {
   auto it = m->packed.find(key);
   if (it != m->packed.end()) return it->second;
   PF_CHECK(m->packing, "packed weight '%s' was not prepared by pf_unet_finalize", key.c_str());
@@ -283,7 +284,7 @@ static PackedW& W(pf_unet* m, const std::string& key, const std::vector<std::str
   for (auto& n : names) {
     const RawTensor& r = raw(m, n);
     launch_pack_weight(r.ptr, pw.hi, pw.lo, static_cast<int>(r.shape[0]), K, taps, rows, row0,
-                       m->pack_stream);
+                       geglu_gran, m->pack_stream);
     row0 += static_cast<int>(r.shape[0]);
   }
   return m->packed[key] = pw;
@@ -307,6 +308,7 @@ static const std::pair<CUtensorMap, CUtensorMap>& wmaps(PackedW& w, int bn, bool
 struct T {  // fp32 NHWC activation
   float* p = nullptr;
   int C = 0, H = 0, W = 0;
+  double* stats = nullptr;  // per-(sample, channel) sum / sum-of-squares [B][C][2], if produced
 };
 
 struct Builder {
@@ -349,29 +351,39 @@ struct Builder {
   }
 
   // ---------------------------------------------------------------- elementwise emitters
+  double* new_stats(int C) {
+    double* acc = gn_pool + gn_used;
+    gn_used += static_cast<size_t>(B) * C * 2;
+    PF_CHECK(dry || gn_used <= gn_pool_doubles, "GN statistics pool overflow");
+    return acc;
+  }
+
+  // statistics of a tensor: taken from the producing GEMM's epilogue when available, otherwise a
+  // dedicated reduction pass
+  const double* stats_of(const T& x) {
+    if (x.stats) return x.stats;
+    PF_CHECK(x.C % 4 == 0 && 256 % (x.C / 4) == 0 && x.C <= 256, "gn_stats: unsupported C=%d", x.C);
+    double* acc = new_stats(x.C);
+    Op& op = push(OP_GN_STATS);
+    op.p[0] = x.p;
+    op.o[0] = acc;
+    op.i[0] = B; op.i[1] = x.H * x.W; op.i[2] = x.C; op.i[3] = x.C; op.i[4] = 0;
+    return acc;
+  }
+
   void gn_scale_shift(const T& x0, const T* x1, const std::string& gname, const std::string& bname,
                       float eps, float*& scale, float*& shift) {
     const int C = x0.C + (x1 ? x1->C : 0);
     const int HW = x0.H * x0.W;
     PF_CHECK(C % 32 == 0, "GroupNorm channels %d not divisible by 32", C);
-    double* acc = gn_pool + gn_used;
-    gn_used += static_cast<size_t>(B) * C * 2;
-    PF_CHECK(dry || gn_used <= gn_pool_doubles, "GN accumulator pool overflow");
-    auto stats = [&](const T& x, int coff) {
-      PF_CHECK(x.C % 4 == 0 && 256 % (x.C / 4) == 0 && x.C <= 256, "gn_stats: unsupported C=%d", x.C);
-      Op& op = push(OP_GN_STATS);
-      op.p[0] = x.p;
-      op.o[0] = acc;
-      op.i[0] = B; op.i[1] = HW; op.i[2] = x.C; op.i[3] = C; op.i[4] = coff;
-    };
-    stats(x0, 0);
-    if (x1) stats(*x1, x0.C);
+    const double* a0 = stats_of(x0);
+    const double* a1 = x1 ? stats_of(*x1) : nullptr;
     scale = alloc<float>(static_cast<size_t>(B) * C);
     shift = alloc<float>(static_cast<size_t>(B) * C);
     Op& op = push(OP_GN_FINALIZE);
-    op.p[0] = acc; op.p[1] = F(m, gname); op.p[2] = F(m, bname);
+    op.p[0] = a0; op.p[1] = F(m, gname); op.p[2] = F(m, bname); op.p[3] = a1;
     op.o[0] = scale; op.o[1] = shift;
-    op.i[0] = B; op.i[1] = HW; op.i[2] = C; op.i[3] = 32;
+    op.i[0] = B; op.i[1] = HW; op.i[2] = C; op.i[3] = 32; op.i[4] = x0.C;
     op.f = eps;
   }
 
@@ -468,7 +480,9 @@ struct Builder {
   }
 
   void out_f32(Op& op, float* out, int ldc, const float* addvec, long long addvec_ld,
-               const float* resid, long long ldr) {
+               const float* resid, long long ldr, double* stats = nullptr) {
+    op.g.stats = stats;
+    op.g.stats_ld = ldc;
     op.g.mode = OUT_F32;
     op.g.out = out;
     op.g.ldc = ldc;
@@ -497,7 +511,8 @@ struct Builder {
       ASrc a{a1, C, Wd, H, B, 1};
       Op& op = conv_gemm(a, w, nullptr, nullptr, H, Wd, L.cout);
       // addvec = Linear(SiLU(t_emb)) + emb bias + conv1 bias  (unet.py:308-316)
-      out_f32(op, h1.p, L.cout, emb_all + L.emb_off, m->emb_total, nullptr, 0);
+      h1.stats = new_stats(L.cout);
+      out_f32(op, h1.p, L.cout, emb_all + L.emb_off, m->emb_total, nullptr, 0, h1.stats);
     }
     free_split(a1);
     gn_scale_shift(h1, nullptr, L.name + ".out_layers.0.weight", L.name + ".out_layers.0.bias", 1e-5f, sc, sh);
@@ -508,6 +523,7 @@ struct Builder {
     T y;
     y.C = L.cout; y.H = H; y.W = Wd;
     y.p = alloc<float>(npix * L.cout);
+    y.stats = new_stats(L.cout);
     PackedW& w2 = W(m, L.name + ".out_layers.3.weight", {L.name + ".out_layers.3.weight"});
     ASrc s2{a2, L.cout, Wd, H, B, 1};
     if (L.cin != L.cout) {
@@ -516,12 +532,12 @@ struct Builder {
       ASrc s3{a3, C, Wd, H, B, 0};
       Op& op = conv_gemm(s2, w2, &s3, &ws, H, Wd, L.cout);
       out_f32(op, y.p, L.cout, Fsum(m, L.name + ".out_layers.3.bias", L.name + ".skip_connection.bias"),
-              0, nullptr, 0);
+              0, nullptr, 0, y.stats);
       free_split(a3);
     } else {
       PF_CHECK(!x1, "identity skip with concatenated input");
       Op& op = conv_gemm(s2, w2, nullptr, nullptr, H, Wd, L.cout);
-      out_f32(op, y.p, L.cout, F(m, L.name + ".out_layers.3.bias"), 0, x0.p, x0.C);
+      out_f32(op, y.p, L.cout, F(m, L.name + ".out_layers.3.bias"), 0, x0.p, x0.C, y.stats);
     }
     free_split(a2);
     return y;
@@ -754,22 +770,22 @@ struct Builder {
       // ---- feed forward: x = ff(norm3(x)) + x   (GeGLU, unet_attention.py:296-333)
       Split l3 = ln_split(xattn, rows, C, tb + ".norm3");
       const int Fh = 4 * C;
-      float* gg = alloc<float>(rows * 2 * Fh);
-      {
-        ASrc s{l3, C, Wd, H, B, 0};
-        Op& op = conv_gemm(s, W(m, tb + ".ff.net.0.proj.weight", {tb + ".ff.net.0.proj.weight"}),
-                           nullptr, nullptr, H, Wd, 2 * Fh);
-        out_f32(op, gg, 2 * Fh, F(m, tb + ".ff.net.0.proj.bias"), 0, nullptr, 0);
-      }
-      free_split(l3);
       Split e = alloc_split(rows * Fh);
       {
-        Op& op = push(OP_GEGLU);
-        op.p[0] = gg;
-        op.o[0] = e.hi; op.o[1] = e.lo;
-        op.i[0] = rows; op.i[1] = Fh;
+        // GeGLU fused into the projection's epilogue: weight rows are interleaved so every BN-wide
+        // tile holds [BN/2 value | BN/2 gate] columns of the same output features
+        const int bn = choose_bn(2 * Fh);
+        ASrc s{l3, C, Wd, H, B, 0};
+        Op& op = conv_gemm(s, W(m, tb + ".ff.net.0.proj.weight:geglu" + std::to_string(bn / 2),
+                                {tb + ".ff.net.0.proj.weight"}, bn / 2),
+                           nullptr, nullptr, H, Wd, 2 * Fh);
+        op.g.mode = OUT_GEGLU;
+        op.g.out_hi = e.hi; op.g.out_lo = e.lo; op.g.ldc = Fh;
+        op.g.addvec = F(m, tb + ".ff.net.0.proj.bias");
+        op.g.addvec_ld = 0;
+        op.g.geglu_f = Fh;
       }
-      arena.free(gg);
+      free_split(l3);
       float* x3 = alloc<float>(rows * C);
       {
         ASrc s{e, Fh, Wd, H, B, 0};
@@ -793,7 +809,8 @@ struct Builder {
       ASrc s{ao, C, Wd, H, B, 0};
       Op& op = conv_gemm(s, W(m, L.name + ".proj_out.weight", {L.name + ".proj_out.weight"}), nullptr,
                          nullptr, H, Wd, C);
-      out_f32(op, y.p, C, F(m, L.name + ".proj_out.bias"), 0, x.p, C);
+      y.stats = new_stats(C);
+      out_f32(op, y.p, C, F(m, L.name + ".proj_out.bias"), 0, x.p, C, y.stats);
     }
     free_split(ao);
     return y;
@@ -808,7 +825,8 @@ struct Builder {
     ASrc s{a, x.C, y.W, y.H, 4 * B, 2};
     Op& op = conv_gemm(s, W(m, L.name + ".op.weight", {L.name + ".op.weight"}), nullptr, nullptr, y.H,
                        y.W, y.C);
-    out_f32(op, y.p, y.C, F(m, L.name + ".op.bias"), 0, nullptr, 0);
+    y.stats = new_stats(y.C);
+    out_f32(op, y.p, y.C, F(m, L.name + ".op.bias"), 0, nullptr, 0, y.stats);
     free_split(a);
     return y;
   }
@@ -821,7 +839,8 @@ struct Builder {
     ASrc s{a, x.C, y.W, y.H, B, 1};
     Op& op = conv_gemm(s, W(m, L.name + ".conv.weight", {L.name + ".conv.weight"}), nullptr, nullptr,
                        y.H, y.W, y.C);
-    out_f32(op, y.p, y.C, F(m, L.name + ".conv.bias"), 0, nullptr, 0);
+    y.stats = new_stats(y.C);
+    out_f32(op, y.p, y.C, F(m, L.name + ".conv.bias"), 0, nullptr, 0, y.stats);
     free_split(a);
     return y;
   }
@@ -835,14 +854,13 @@ struct Builder {
       size_t doubles = 0;
       auto count_block = [&](const BlockSpec& b) {
         for (auto& l : b.layers) {
-          if (l.kind == Layer::RES) doubles += static_cast<size_t>(B) * (l.cin + l.cout) * 2;
-          if (l.kind == Layer::ST) doubles += static_cast<size_t>(B) * l.cin * 2;
+          if (l.kind == Layer::RES) doubles += static_cast<size_t>(B) * (2 * l.cout) * 2;
+          else doubles += static_cast<size_t>(B) * l.cout * 2;
         }
       };
       for (auto& b : m->input_blocks) count_block(b);
       count_block(m->middle);
       for (auto& b : m->output_blocks) count_block(b);
-      doubles += static_cast<size_t>(B) * c.channels * 2;  // final norm
       gn_pool_doubles = doubles;
       gn_pool = alloc<double>(doubles);
       Op& op = push(OP_MEMSET);
@@ -992,7 +1010,8 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
                         (int)op.i[1], (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
         break;
       case OP_GN_FINALIZE:
-        launch_gn_finalize(static_cast<const double*>(op.p[0]), static_cast<const float*>(op.p[1]),
+        launch_gn_finalize(static_cast<const double*>(op.p[0]), (int)op.i[4],
+                           static_cast<const double*>(op.p[3]), static_cast<const float*>(op.p[1]),
                            static_cast<const float*>(op.p[2]), static_cast<float*>(op.o[0]),
                            static_cast<float*>(op.o[1]), (int)op.i[0], (int)op.i[1], (int)op.i[2],
                            (int)op.i[3], op.f, s);

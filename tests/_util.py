@@ -1,6 +1,8 @@
 """Shared helpers for the parity tests."""
 import torch
 
+_RANDN = torch.randn  # captured before any test monkeypatches torch.randn
+
 SDF_KW = dict(in_channels=2, out_channels=2, channels=64, n_res_blocks=2, attention_levels=[2, 3],
               channel_multipliers=[1, 2, 4, 4], n_heads=4, tf_layers=1)
 
@@ -39,4 +41,4 @@ class NoiseTape:
         self.gen = torch.Generator().manual_seed(seed)
 
     def __call__(self, shape):
-        return torch.randn(tuple(shape), generator=self.gen)
+        return _RANDN(tuple(shape), generator=self.gen)
