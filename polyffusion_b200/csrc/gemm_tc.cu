@@ -1,7 +1,7 @@
 // tcgen05 implicit-GEMM kernel (bf16x3 split precision), see gemm_tc.cuh.
 //
-// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA
-// issuer (one elected lane), warps 2..5 = epilogue (TMEM -> registers -> global).
+// Roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA
+// issuer (one elected lane), warps 2..9 = epilogue (TMEM -> registers -> smem staging -> global).
 // Pipelines: smem ring full[]/empty[] (TMA <-> MMA) and tmem_full[]/tmem_empty[] (MMA <-> epilogue).
 // Persistent: grid = min(#tiles, #SMs); each CTA walks tiles (n fastest, then m, then z) with a
 // static stride.  The TMEM accumulator is double buffered (2 x BN columns) so the epilogue of tile i
@@ -12,7 +12,7 @@
 namespace pf {
 
 constexpr int MAX_STAGES = 8;
-constexpr int STG_PITCH = 36;  // floats per staged row (32 + 4 pad: conflict-free float4 access)
+constexpr int STG_FLOATS = 32 * 32;  // per-warp staging tile: 32 rows x 32 fp32, 16-byte groups XOR-swizzled by row
 
 struct TileCoord {
   int n0, tile, zb, zh, img, trem, x0, y0;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[i]), 8);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -153,23 +153,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue (8 warps)
     // TMEM -> registers (thread = output row) -> per-warp smem staging -> coalesced global stores:
     // in the store phase a quarter-warp (8 lanes x float4) covers one 128-byte row segment, so
-    // every store / residual load touches whole 128 B lines.  Optional per-channel sum / sum-of-
-    // squares of the stored values (GroupNorm statistics for the consumer) are reduced in
-    // registers -> shuffles -> smem atomics -> one fp64 atomicAdd per (tile, column).
-    const int q = warp & 3;       // TMEM lane quarter this warp may access
-    const int ewarp = warp - 2;   // 0..3
-    float* stg = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw)) + nstages * STAGE_BYTES) +
-                 ewarp * (32 * STG_PITCH);
-    float* sacc = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw)) + nstages * STAGE_BYTES) +
-                  4 * 32 * STG_PITCH;  // [2 parity][2][BN]
-    const int et = threadIdx.x - 64;  // 0..127 among epilogue threads
-    if (p.stats) {
-      for (int i = et; i < 4 * BN; i += 128) sacc[i] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
+    // every store / residual load touches whole 128 B lines.  Two warps share each TMEM lane
+    // quarter and take alternate 32-column chunks.  Residual values are prefetched into registers
+    // before the TMEM load so their DRAM latency overlaps the TMEM/smem round trip.  Optional
+    // per-channel sum / sum-of-squares of the stored values (GroupNorm statistics for the consumer)
+    // are reduced in registers -> shuffles -> smem -> one fp64 atomicAdd per (tile, column).
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int ewarp = warp - 2;        // 0..7
+    const int chalf = ewarp >> 2;      // which alternate chunks this warp takes
+    uint8_t* epi_base = smem_raw + (ring - smem_u32(smem_raw)) + nstages * STAGE_BYTES;
+    float* stg_all = reinterpret_cast<float*>(epi_base);
+    float* stg = stg_all + ewarp * STG_FLOATS;
+    const int et = threadIdx.x - 64;   // 0..255 among epilogue threads
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     int lt = 0;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
@@ -182,14 +180,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
       const long long m0 = static_cast<long long>(tc.tile) * GEMM_BM + q * 32;  // first row of this warp
       const long long zoff = tc.zb * p.out_zb + tc.zh * p.out_zh;
-      float* sa = sacc + as * 2 * BN;
 
       if (p.mode == OUT_SPLIT_T) {
         // [img][n][token]; consecutive lanes -> consecutive tokens (already coalesced)
         const long long tok = static_cast<long long>(tc.trem) * GEMM_BM + q * 32 + lane;
         const long long base = zoff + static_cast<long long>(tc.img) * p.out_img + tok;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = chalf * 32; c < BN; c += 64) {
           uint32_t v[32];
           tmem_ld32(taddr + c, v);
           tmem_ld_wait();
@@ -207,8 +204,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int ncols = geglu ? BN / 2 : BN;          // output columns produced by this tile
         const int ocol0 = geglu ? (tc.n0 / 2) : tc.n0;  // first output column
         const float* av = p.addvec ? p.addvec + static_cast<long long>(tc.img) * p.addvec_ld : nullptr;
-#pragma unroll 1
-        for (int c = 0; c < ncols; c += 32) {
+        const bool has_res = (p.mode == OUT_F32) && p.resid != nullptr;
+        float4 csum[BN / 64], csq[BN / 64];  // per-chunk column partial sums (lanes < 8 after shuffles)
+#pragma unroll
+        for (int ci = 0; ci < BN / 64; ++ci) {
+          const int c = chalf * 32 + ci * 64;
+          if (c >= ncols) break;
+          float4 rres[8];
+          if (has_res) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              rres[it] = __ldg(reinterpret_cast<const float4*>(
+                  p.resid + (m0 + it * 4 + rsub) * p.ldr + tc.n0 + c + c4));
+          }
           {
             uint32_t v[32];
             tmem_ld32(taddr + c, v);
@@ -218,23 +226,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               tmem_ld_wait();
               // value = cols [ocol0 + c, +32) of the first half, gate = same cols of the second
               // half of the (un-interleaved) projection: out = (x + b_x) * gelu(g + b_g)
+              const float4* bx = reinterpret_cast<const float4*>(av + ocol0 + c);
+              const float4* bg = reinterpret_cast<const float4*>(av + p.geglu_f + ocol0 + c);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float xv = __uint_as_float(v[j]) + __ldg(av + ocol0 + c + j);
-                const float gv = __uint_as_float(g[j]) + __ldg(av + p.geglu_f + ocol0 + c + j);
-                v[j] = __float_as_uint(xv * (0.5f * gv * (1.0f + erff(gv * 0.70710678118654752440f))));
+              for (int j = 0; j < 8; ++j) {
+                const float4 b1 = __ldg(bx + j), b2 = __ldg(bg + j);
+                const float bxv[4] = {b1.x, b1.y, b1.z, b1.w}, bgv[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float xv = __uint_as_float(v[4 * j + k]) + bxv[k];
+                  const float gv = __uint_as_float(g[4 * j + k]) + bgv[k];
+                  v[4 * j + k] =
+                      __float_as_uint(xv * (0.5f * gv * (1.0f + erff(gv * 0.70710678118654752440f))));
+                }
               }
             } else {
               tmem_ld_wait();
               if (av) {
+                const float4* b4 = reinterpret_cast<const float4*>(av + tc.n0 + c);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(av + tc.n0 + c + j));
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = __ldg(b4 + j);
+                  v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+                  v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+                  v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+                  v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+                }
               }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + 4 * j) =
+              *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                   make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           __syncwarp();
@@ -242,12 +264,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int row = it * 4 + rsub;
-            float4 o = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + c4);
+            float4 o = *reinterpret_cast<const float4*>(stg + row * 32 + (((lane & 7) ^ (row & 7)) << 2));
             const long long m = m0 + row;
             if (p.mode == OUT_F32) {
-              if (p.resid) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(p.resid + m * p.ldr + tc.n0 + c + c4));
-                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              if (has_res) {
+                o.x += rres[it].x; o.y += rres[it].y; o.z += rres[it].z; o.w += rres[it].w;
               }
               *reinterpret_cast<float4*>(p.out + zoff + m * p.ldc + tc.n0 + c + c4) = o;
               ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
@@ -263,7 +284,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
           }
           if (p.stats) {
-            // reduce over the 4 row-groups of the warp (lanes with equal lane&7), then smem atomics
+            // reduce over the 4 row-groups of the warp (lanes with equal lane&7)
 #pragma unroll
             for (int o = 8; o <= 16; o <<= 1) {
               ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, o);
@@ -275,15 +296,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, o);
               ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, o);
             }
-            if (lane < 8) {
-              float* d = sa + c + c4;
-              atomicAdd(d + 0, ssum.x); atomicAdd(d + 1, ssum.y);
-              atomicAdd(d + 2, ssum.z); atomicAdd(d + 3, ssum.w);
-              atomicAdd(d + BN + 0, ssq.x); atomicAdd(d + BN + 1, ssq.y);
-              atomicAdd(d + BN + 2, ssq.z); atomicAdd(d + BN + 3, ssq.w);
-            }
+            csum[ci] = ssum;
+            csq[ci] = ssq;
           }
           __syncwarp();
+        }
+        if (p.stats && lane < 8) {
+          // park the partials in this warp's (now idle) staging tile: [chunk][sum | sq][32 cols]
+#pragma unroll
+          for (int ci = 0; ci < BN / 64; ++ci) {
+            *reinterpret_cast<float4*>(stg + (ci * 2 + 0) * 32 + c4) = csum[ci];
+            *reinterpret_cast<float4*>(stg + (ci * 2 + 1) * 32 + c4) = csq[ci];
+          }
         }
       }
       // all of this warp's TMEM reads for the tile are complete (tmem_ld_wait above)
@@ -292,15 +316,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
       if (p.stats) {
         // flush this tile's column sums: [img][stats_ld][2] fp64
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int col = et; col < BN; col += 128) {
-          const float s1 = sa[col], s2 = sa[BN + col];
-          sa[col] = 0.f;
-          sa[BN + col] = 0.f;
-          double* d = p.stats + (static_cast<long long>(tc.img) * p.stats_ld + tc.n0 + col) * 2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et < BN) {
+          // column et lives in chunk et/32: warps (chunk&1)*4 + quarter, local chunk index chunk>>1
+          const int chunk = et >> 5, cl = et & 31;
+          const float* src = stg_all + ((chunk & 1) * 4) * STG_FLOATS + ((chunk >> 1) * 2) * 32 + cl;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            s1 += src[qq * STG_FLOATS];
+            s2 += src[qq * STG_FLOATS + 32];
+          }
+          double* d = p.stats + (static_cast<long long>(tc.img) * p.stats_ld + tc.n0 + et) * 2;
           atomicAdd(d, static_cast<double>(s1));
           atomicAdd(d + 1, static_cast<double>(s2));
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
   }

@@ -19,7 +19,7 @@ namespace pf {
 
 constexpr int GEMM_BM = 128;      // output rows (pixels / tokens) per CTA
 constexpr int GEMM_BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192; // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int GEMM_THREADS = 320; // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int GEMM_MAX_TAPS = 12;
 
 enum GemmOutMode : int {
@@ -67,8 +67,8 @@ struct alignas(64) GemmParams {
 // smem bytes for a given BN / stage count (incl. 1 KB alignment slack)
 inline int gemm_stage_bytes(int bn) { return 2 * GEMM_BM * 128 + 2 * bn * 128; }
 inline int gemm_smem_bytes(int bn, int nstages) { return nstages * gemm_stage_bytes(bn) + 1024; }
-// epilogue staging (4 warps x 32 rows x 36 floats) + column-statistics accumulators [2][2][bn]
-inline int gemm_epilogue_smem_bytes(int bn) { return 4 * 32 * 36 * 4 + 4 * bn * 4; }
+// epilogue staging: 8 warps x (32 rows x 32 fp32)
+inline int gemm_epilogue_smem_bytes(int /*bn*/) { return 8 * 32 * 32 * 4; }
 
 // persistent launch: min(#tiles, num_ctas) CTAs
 cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t stream);

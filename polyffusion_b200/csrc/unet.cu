@@ -940,6 +940,8 @@ struct Builder {
             op.p[1] = F(m, l.name + ".weight"); op.p[2] = F(m, l.name + ".bias");
             op.o[0] = nxt.p;
             op.i[0] = B; op.i[1] = l.cin; op.i[2] = H; op.i[3] = Wd; op.i[4] = l.cout;
+            // its GroupNorm statistics are needed twice (next ResBlock, last skip): reduce once
+            nxt.stats = const_cast<double*>(stats_of(nxt));
             break;
           }
           case Layer::RES: nxt = res_block(l, cur, first ? skip : nullptr); break;
