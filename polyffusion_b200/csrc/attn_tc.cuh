@@ -1,0 +1,28 @@
+// Fused tcgen05 attention core (see attn_tc.cu): parameter block shared by host and device.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace pf {
+
+constexpr int ATTN_THREADS = 320;
+
+struct alignas(64) AttnParams {
+  CUtensorMap q_hi, q_lo;  // split-bf16 queries, 2-D {ldq, B*N}, box {64, 128}
+  CUtensorMap k_hi, k_lo;  // split-bf16 keys,    2-D {ldk, B*Nk}, box {64, 64}
+  CUtensorMap v_hi, v_lo;  // split-bf16 V^T,     2-D {Nk, B*heads*64}, box {64, 64}
+  int B, heads, N, Nk;     // N % 128 == 0, Nk % 64 == 0, d_head == 64
+  int qcol0, kcol0, ocol0; // column of head 0 inside the q / k / o row
+  float scale_log2e;       // d_head^-0.5 * log2(e)
+  __nv_bfloat16* o_hi;     // split-bf16 output [B*N, ldo], head h at columns ocol0 + h*64
+  __nv_bfloat16* o_lo;
+  long long ldo;
+};
+
+int attn_smem_bytes();
+cudaError_t attn_init_attrs();
+cudaError_t launch_attn(const AttnParams& p, int num_ctas, cudaStream_t stream);
+
+}  // namespace pf

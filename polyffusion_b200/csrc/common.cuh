@@ -149,6 +149,21 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
          (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
+// GELU(erf) with the Abramowitz-Stegun 7.1.26 rational approximation of erf (|abs err| <= 1.5e-7,
+// i.e. at fp32 resolution) instead of erff: ~4x fewer instructions in the GeGLU epilogue.
+__device__ __forceinline__ float gelu_erf_fast(float g) {
+  const float z = fabsf(g) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = 1.0f - poly * __expf(-z * z);
+  const float erf_v = copysignf(erf_abs, g);
+  return 0.5f * g * (1.0f + erf_v);
+}
+
 // ---------------------------------------------------------------- bf16 hi/lo split
 // x ~= hi + lo with hi = rn_bf16(x), lo = rn_bf16(x - hi): 16 mantissa bits kept.
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {

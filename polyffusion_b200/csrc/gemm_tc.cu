@@ -236,8 +236,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 for (int k = 0; k < 4; ++k) {
                   const float xv = __uint_as_float(v[4 * j + k]) + bxv[k];
                   const float gv = __uint_as_float(g[4 * j + k]) + bgv[k];
-                  v[4 * j + k] =
-                      __float_as_uint(xv * (0.5f * gv * (1.0f + erff(gv * 0.70710678118654752440f))));
+                  v[4 * j + k] = __float_as_uint(xv * gelu_erf_fast(gv));
                 }
               }
             } else {

@@ -7,6 +7,9 @@
 namespace pf {
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+// SiLU on the operand-transform path: ex2.approx + rcp (relative error ~1e-6, an order of magnitude
+// below the 2^-16 operand rounding that follows)
+__device__ __forceinline__ float silu_fast(float v) { return v * __frcp_rn(1.0f + __expf(-v)); }
 
 // ------------------------------------------------------------------------------------------------
 // conv_in: NCHW fp32 (tiny Cin) -> NHWC fp32, 3x3 pad 1.
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(256) act_split_kernel(
   }
   if (silu) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+    for (int i = 0; i < 8; ++i) v[i] = silu_fast(v[i]);
   }
   uint4 h, l;
   split2(v[0], v[1], h.x, l.x);

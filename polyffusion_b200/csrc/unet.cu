@@ -17,6 +17,7 @@
 #include <unordered_map>
 
 #include "../../include/pf_b200.h"
+#include "attn_tc.cuh"
 #include "host_util.h"
 
 namespace pf {
@@ -56,7 +57,7 @@ struct BlockSpec {
 
 enum OpKind {
   OP_GEMM, OP_CONV_IN, OP_GN_STATS, OP_GN_FINALIZE, OP_ACT_SPLIT, OP_LN_SPLIT, OP_GEGLU, OP_SOFTMAX,
-  OP_TIME_SIN, OP_SMALL_LINEAR, OP_CONV_OUT, OP_MEMSET
+  OP_TIME_SIN, OP_SMALL_LINEAR, OP_CONV_OUT, OP_MEMSET, OP_ATTN
 };
 enum ExtSlot { EXT_NONE = 0, EXT_X, EXT_T, EXT_COND, EXT_OUT };
 
@@ -65,6 +66,7 @@ struct Op {
   int ext = EXT_NONE;
   int bn = 0;
   GemmParams g;
+  AttnParams a;
   const void* p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void* o[2] = {nullptr, nullptr};
   long long i[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -347,6 +349,7 @@ struct Builder {
     Op& op = plan->ops.back();
     op.kind = k;
     memset(&op.g, 0, sizeof op.g);
+    memset(&op.a, 0, sizeof op.a);
     return op;
   }
 
@@ -549,6 +552,27 @@ struct Builder {
                       const Split& vt, int N, int Nq_w, int Nq_h, int Nk, int heads, Split& o,
                       int ldo) {
     const int Z = B * heads;
+    static const bool unfused = std::getenv("PF_ATTN_UNFUSED") != nullptr;
+    if (!unfused) {
+      // fused tcgen05 kernel: scores / probabilities stay in TMEM / smem (attn_tc.cu)
+      PF_CHECK(N % 128 == 0 && Nk % 64 == 0, "attention: unsupported shape N=%d Nk=%d", N, Nk);
+      Op& op = push(OP_ATTN);
+      AttnParams& a = op.a;
+      if (!dry) {
+        a.q_hi = make_map_2d(q.hi, ldq, static_cast<long long>(B) * N, 128);
+        a.q_lo = make_map_2d(q.lo, ldq, static_cast<long long>(B) * N, 128);
+        a.k_hi = make_map_2d(k.hi, ldk, static_cast<long long>(B) * Nk, 64);
+        a.k_lo = make_map_2d(k.lo, ldk, static_cast<long long>(B) * Nk, 64);
+        a.v_hi = make_map_2d(vt.hi, Nk, static_cast<long long>(Z) * 64, 64);
+        a.v_lo = make_map_2d(vt.lo, Nk, static_cast<long long>(Z) * 64, 64);
+      }
+      a.B = B; a.heads = heads; a.N = N; a.Nk = Nk;
+      a.qcol0 = qcol0; a.kcol0 = kcol0; a.ocol0 = 0;
+      a.scale_log2e = 0.125f * 1.4426950408889634f;  // d_head ** -0.5 (unet_attention.py:157) * log2(e)
+      a.o_hi = o.hi; a.o_lo = o.lo; a.ldo = ldo;
+      (void)Nq_w; (void)Nq_h;
+      return;
+    }
     PF_CHECK(Nk % 128 == 0 && Nk <= 1024, "attention: unsupported key count %d", Nk);
     float* S = alloc<float>(static_cast<size_t>(Z) * N * Nk);
     {
@@ -999,6 +1023,9 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
       case OP_MEMSET:
         PF_CUDA(cudaMemsetAsync(op.o[0], 0, static_cast<size_t>(op.i[0]), s));
         break;
+      case OP_ATTN:
+        PF_CUDA(launch_attn(op.a, m->num_sms, s));
+        break;
       case OP_GEMM:
         PF_CUDA(launch_gemm(op.g, op.bn, m->num_sms, s));
         break;
@@ -1107,6 +1134,7 @@ int pf_unet_create(const pf_unet_cfg* cfg, pf_unet** out) {
              prop.minor);
     m->num_sms = prop.multiProcessorCount;
     PF_CUDA(gemm_init_attrs());
+    PF_CUDA(attn_init_attrs());
     build_graph(m.get());
     *out = m.release();
   });
@@ -1208,6 +1236,10 @@ int pf_unet_forward_profiled(pf_unet* h, const float* x, const int64_t* time_ste
       PF_CUDA(cudaEventElapsedTime(&op_ms_host[i], ev[i], ev[i + 1]));
       op_kind_host[i] = static_cast<int32_t>(plan->ops[i].kind);
       op_flops_host[i] = plan->ops[i].kind == OP_GEMM ? gemm_flops(plan->ops[i]) : 0.0;
+      if (plan->ops[i].kind == OP_ATTN) {  // algorithmic: QK^T + PV, 2*N*Nk*64 each per (b, head)
+        const AttnParams& a = plan->ops[i].a;
+        op_flops_host[i] = 4.0 * a.B * a.heads * static_cast<double>(a.N) * a.Nk * 64;
+      }
     }
     for (auto& e : ev) cudaEventDestroy(e);
     *n_ops = static_cast<int32_t>(n);
@@ -1252,7 +1284,8 @@ int pf_unet_op_desc(pf_unet* h, int32_t i, char* buf, int32_t len) {
     PF_CHECK(i >= 0 && static_cast<size_t>(i) < h->last_plan->ops.size(), "op index out of range");
     const Op& op = h->last_plan->ops[i];
     static const char* names[] = {"gemm", "conv_in", "gn_stats", "gn_finalize", "act_split", "ln_split",
-                                  "geglu", "softmax", "time_sin", "small_linear", "conv_out", "memset"};
+                                  "geglu", "softmax", "time_sin", "small_linear", "conv_out", "memset",
+                                  "attn"};
     if (op.kind == OP_GEMM) {
       const GemmParams& g = op.g;
       int k = 0;
@@ -1260,6 +1293,8 @@ int pf_unet_op_desc(pf_unet* h, int32_t i, char* buf, int32_t len) {
       snprintf(buf, len, "gemm M=%lld N=%d K=%d bn=%d taps=%d nseg=%d z=%d mode=%d stages=%d",
                static_cast<long long>(g.m_tiles) * 128, g.n_tiles * op.bn, k, op.bn, g.seg[0].ntaps,
                g.nseg, g.z_count, g.mode, g.nstages);
+    } else if (op.kind == OP_ATTN) {
+      snprintf(buf, len, "attn B=%d heads=%d N=%d Nk=%d", op.a.B, op.a.heads, op.a.N, op.a.Nk);
     } else {
       snprintf(buf, len, "%s i=[%lld,%lld,%lld,%lld,%lld,%lld,%lld]", names[op.kind], op.i[0], op.i[1],
                op.i[2], op.i[3], op.i[4], op.i[5], op.i[6]);
@@ -1333,6 +1368,7 @@ struct TempModel {
     PF_CHECK(prop.major == 10, "this library targets sm_100a (B200); found sm_%d%d", prop.major, prop.minor);
     m.num_sms = prop.multiProcessorCount;
     PF_CUDA(gemm_init_attrs());
+    PF_CUDA(attn_init_attrs());
     m.packing = true;
   }
   ~TempModel() {
