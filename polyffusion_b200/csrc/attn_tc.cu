@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
         uint32_t ph[16], pl[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), c, -mc));
-          const float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
+          const float p0 = fast_ex2(fmaf(__uint_as_float(v[2 * i]), c, -mc));
+          const float p1 = fast_ex2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
           sum += p0 + p1;
           split2(p0, p1, ph[i], pl[i]);
         }

@@ -149,17 +149,29 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
          (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
+// Branch-free MUFU wrappers (ex2.approx / rcp.approx: ~2^-22 relative error, no slow paths)
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // GELU(erf) with the Abramowitz-Stegun 7.1.26 rational approximation of erf (|abs err| <= 1.5e-7,
 // i.e. at fp32 resolution) instead of erff: ~4x fewer instructions in the GeGLU epilogue.
 __device__ __forceinline__ float gelu_erf_fast(float g) {
   const float z = fabsf(g) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float erf_abs = 1.0f - poly * __expf(-z * z);
+  const float erf_abs = 1.0f - poly * fast_ex2(-1.4426950408889634f * z * z);
   const float erf_v = copysignf(erf_abs, g);
   return 0.5f * g * (1.0f + erf_v);
 }
@@ -167,20 +179,26 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
 // ---------------------------------------------------------------- bf16 hi/lo split
 // x ~= hi + lo with hi = rn_bf16(x), lo = rn_bf16(x - hi): 16 mantissa bits kept.
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(x, 0.f);
+  const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+  const __nv_bfloat162 l2 = __floats2bfloat162_rn(x - __uint_as_float(hb << 16), 0.f);
+  const uint32_t lb = *reinterpret_cast<const uint32_t*>(&l2);
+  hi = __ushort_as_bfloat16(static_cast<unsigned short>(hb & 0xffffu));
+  lo = __ushort_as_bfloat16(static_cast<unsigned short>(lb & 0xffffu));
 }
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return static_cast<uint32_t>(__bfloat16_as_ushort(a)) |
          (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
 }
-// split 2 floats -> packed hi pair and packed lo pair
+// split 2 floats -> packed hi pair and packed lo pair (low 16 bits = first element).
+// Uses the packed cvt.rn.bf16x2.f32 (F2FP, full-rate ALU op) rather than two scalar F2F conversions.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 ah, al, bh, bl;
-  split_bf16(a, ah, al);
-  split_bf16(b, bh, bl);
-  hi = pack_bf16(ah, bh);
-  lo = pack_bf16(al, bl);
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h2);
+  const float ah = __uint_as_float(hi << 16);
+  const float bh = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - ah, b - bh);
+  lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
 }  // namespace pf

@@ -174,12 +174,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const TileCoord tc = decode_tile(p, t, BN);
       const int as = lt & 1;
       const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
+      const long long m0 = static_cast<long long>(tc.tile) * GEMM_BM + q * 32;  // first row of this warp
+      const long long zoff = tc.zb * p.out_zb + tc.zh * p.out_zh;
+      if (p.mode == OUT_F32 && p.resid != nullptr) {
+        // pull this warp's share of the residual tile into L2 while the main loop is still running
+        // (one 128-byte line per (row, 32-column chunk)); the register prefetch below then hits L2
+#pragma unroll
+        for (int ci = 0; ci < BN / 64; ++ci) {
+          const float* ptr = p.resid + (m0 + lane) * p.ldr + tc.n0 + chalf * 32 + ci * 64;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        }
+      }
       mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
       tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-      const long long m0 = static_cast<long long>(tc.tile) * GEMM_BM + q * 32;  // first row of this warp
-      const long long zoff = tc.zb * p.out_zb + tc.zh * p.out_zh;
 
       if (p.mode == OUT_SPLIT_T) {
         // [img][n][token]; consecutive lanes -> consecutive tokens (already coalesced)

@@ -9,7 +9,9 @@ namespace pf {
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
 // SiLU on the operand-transform path: ex2.approx + rcp (relative error ~1e-6, an order of magnitude
 // below the 2^-16 operand rounding that follows)
-__device__ __forceinline__ float silu_fast(float v) { return v * __frcp_rn(1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_fast(float v) {
+  return v * fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * v));
+}
 
 // ------------------------------------------------------------------------------------------------
 // conv_in: NCHW fp32 (tiny Cin) -> NHWC fp32, 3x3 pad 1.
