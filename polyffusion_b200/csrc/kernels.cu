@@ -44,20 +44,28 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   const int cpq = Cout / 4;  // channels per quarter (16 for Cout = 64)
   if (xb + p >= W) return;
   float* o = out + ((static_cast<long long>(b) * H + y) * W + xb + p) * Cout + q * cpq;
-  for (int c0 = 0; c0 < cpq; c0 += 4) {
-    float4 acc = *reinterpret_cast<const float4*>(bias + q * cpq + c0);
-    for (int ci = 0; ci < Cin; ++ci)
-      for (int r = 0; r < 3; ++r)
-        for (int kx = 0; kx < 3; ++kx) {
-          const float v = sx[(ci * 3 + r) * 66 + p + kx];
-          const float4 ww = *reinterpret_cast<const float4*>(sw + (ci * 9 + r * 3 + kx) * Cout + q * cpq + c0);
-          acc.x = fmaf(v, ww.x, acc.x);
-          acc.y = fmaf(v, ww.y, acc.y);
-          acc.z = fmaf(v, ww.z, acc.z);
-          acc.w = fmaf(v, ww.w, acc.w);
+  // cpq == 16 (checked by the host): 16 accumulators per thread, weights broadcast from smem
+  float4 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = *reinterpret_cast<const float4*>(bias + q * 16 + 4 * j);
+  for (int ci = 0; ci < Cin; ++ci)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float v = sx[(ci * 3 + r) * 66 + p + kx];
+        const float* wr = sw + (ci * 9 + r * 3 + kx) * Cout + q * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 ww = *reinterpret_cast<const float4*>(wr + 4 * j);
+          acc[j].x = fmaf(v, ww.x, acc[j].x);
+          acc[j].y = fmaf(v, ww.y, acc[j].y);
+          acc[j].z = fmaf(v, ww.z, acc[j].z);
+          acc[j].w = fmaf(v, ww.w, acc[j].w);
         }
-    *reinterpret_cast<float4*>(o + c0) = acc;
-  }
+      }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(o + 4 * j) = acc[j];
 }
 
 void launch_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int Cin,
@@ -117,115 +125,112 @@ void launch_gn_stats(const float* src, double* acc, int B, int HW, int Cs, int C
   gn_stats_kernel<<<grid, 256, 0, s>>>(src, acc, HW, Cs, Ctot, coff, ppb);
 }
 
-__global__ void gn_finalize_kernel(const double* __restrict__ acc0, int C0,
-                                   const double* __restrict__ acc1, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ scale,
-                                   float* __restrict__ shift, int HW, int Ctot, int groups,
-                                   float eps) {
-  // channel statistics of the (virtually) concatenated tensor: channels [0, C0) come from acc0
-  // [B][C0][2], channels [C0, Ctot) from acc1 [B][Ctot-C0][2]
-  const int b = blockIdx.x;
-  const int cpg = Ctot / groups;
-  const int C1 = Ctot - C0;
-  for (int c = threadIdx.x; c < Ctot; c += blockDim.x) {
-    const int g = c / cpg;
-    double ts = 0.0, tq = 0.0;
-    for (int i = 0; i < cpg; ++i) {
-      const int ch = g * cpg + i;
-      const double* a = ch < C0 ? acc0 + (static_cast<long long>(b) * C0 + ch) * 2
-                                : acc1 + (static_cast<long long>(b) * C1 + (ch - C0)) * 2;
-      ts += a[0];
-      tq += a[1];
-    }
-    const double n = static_cast<double>(HW) * cpg;
-    const double mean = ts / n;
-    double var = tq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float sc = gamma[c] * rstd;
-    scale[static_cast<long long>(b) * Ctot + c] = sc;
-    shift[static_cast<long long>(b) * Ctot + c] = beta[c] - static_cast<float>(mean) * sc;
-  }
-}
-
-void launch_gn_finalize(const double* acc0, int C0, const double* acc1, const float* gamma,
-                        const float* beta, float* scale, float* shift, int B, int HW, int Ctot,
-                        int groups, float eps, cudaStream_t s) {
-  gn_finalize_kernel<<<B, 256, 0, s>>>(acc0, C0, acc1, gamma, beta, scale, shift, HW, Ctot, groups, eps);
-}
-
 // ------------------------------------------------------------------------------------------------
-// act_split: fp32 NHWC (one or two concatenated sources) -> split bf16 operand tensor
-// one thread = 8 channels of one pixel
+// act_split: fp32 NHWC (one or two concatenated sources) -> split bf16 operand tensor(s).
+// GroupNorm is finalised in the block prologue from the per-(sample, channel) fp64 sums the
+// producing GEMM epilogues left behind (no separate finalize launch): scale/shift for the block's
+// sample go to smem.  One thread-item = 16 channels of one pixel (4 x 16-byte loads in flight).
+// Optional second output = plain split of the same input (operand of the ResBlock 1x1 skip conv).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) act_split_kernel(
-    const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
-    const float* __restrict__ scale, const float* __restrict__ shift, int silu, int layout,
-    bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int H, int W) {
-  const int C = C0 + C1;
-  const int c8n = C >> 3;
-  const long long total = static_cast<long long>(B) * H * W * c8n;
-  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int c = static_cast<int>(idx % c8n) * 8;
-  const long long pix = idx / c8n;  // b*H*W + y*W + x
-  const int b = static_cast<int>(pix / (static_cast<long long>(H) * W));
-  float v[8];
-  {
-    const float* sp = (c < C0) ? src0 + pix * C0 + c : src1 + pix * C1 + (c - C0);
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(sp));
-    const float4 a1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
-    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
-    v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+constexpr int AS_IPT = 4;  // items per thread
+
+__device__ __forceinline__ void store_split16(const float* v, bf16* oh, bf16* ol) {
+  uint4 h0, l0, h1, l1;
+  split2(v[0], v[1], h0.x, l0.x);   split2(v[2], v[3], h0.y, l0.y);
+  split2(v[4], v[5], h0.z, l0.z);   split2(v[6], v[7], h0.w, l0.w);
+  split2(v[8], v[9], h1.x, l1.x);   split2(v[10], v[11], h1.y, l1.y);
+  split2(v[12], v[13], h1.z, l1.z); split2(v[14], v[15], h1.w, l1.w);
+  reinterpret_cast<uint4*>(oh)[0] = h0;
+  reinterpret_cast<uint4*>(oh)[1] = h1;
+  reinterpret_cast<uint4*>(ol)[0] = l0;
+  reinterpret_cast<uint4*>(ol)[1] = l1;
+}
+
+__global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
+  __shared__ float s_scale[512], s_shift[512];
+  const int C = a.C0 + a.C1;
+  const int b = blockIdx.y;
+  const bool norm = a.stats0 != nullptr;
+  if (norm) {
+    const int cpg = C / a.groups;
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const int g = c / cpg;
+      double ts = 0.0, tq = 0.0;
+      for (int i = 0; i < cpg; ++i) {
+        const int ch = g * cpg + i;
+        const double* st = ch < a.C0 ? a.stats0 + (static_cast<long long>(b) * a.C0 + ch) * 2
+                                     : a.stats1 + (static_cast<long long>(b) * a.C1 + (ch - a.C0)) * 2;
+        ts += st[0];
+        tq += st[1];
+      }
+      const double n = static_cast<double>(a.H) * a.W * cpg;
+      const double mean = ts / n;
+      double var = tq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+      const float sc = a.gamma[c] * rstd;
+      s_scale[c] = sc;
+      s_shift[c] = a.beta[c] - static_cast<float>(mean) * sc;
+    }
+    __syncthreads();
   }
-  if (scale) {
-    const float* sc = scale + static_cast<long long>(b) * C + c;
-    const float* sh = shift + static_cast<long long>(b) * C + c;
+  const int c16n = C >> 4;
+  const int HW = a.H * a.W;
+  const int items = HW * c16n;
+  const long long pix_base = static_cast<long long>(b) * HW;
+#pragma unroll 1
+  for (int k = 0; k < AS_IPT; ++k) {
+    const int item = (blockIdx.x * AS_IPT + k) * 256 + threadIdx.x;
+    if (item >= items) break;
+    const int c = (item % c16n) * 16;
+    const int pl = item / c16n;  // pixel inside the sample
+    const long long pix = pix_base + pl;
+    float v[16];
+    {
+      const float* sp = (c < a.C0) ? a.src0 + pix * a.C0 + c : a.src1 + pix * a.C1 + (c - a.C0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], __ldg(sc + i), __ldg(sh + i));
-  }
-  if (silu) {
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(sp) + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      }
+    }
+    if (a.out2_hi) store_split16(v, a.out2_hi + pix * C + c, a.out2_lo + pix * C + c);
+    if (norm) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = silu_fast(v[i]);
-  }
-  uint4 h, l;
-  split2(v[0], v[1], h.x, l.x);
-  split2(v[2], v[3], h.y, l.y);
-  split2(v[4], v[5], h.z, l.z);
-  split2(v[6], v[7], h.w, l.w);
-  if (layout == XF_SAME) {
-    *reinterpret_cast<uint4*>(out_hi + pix * C + c) = h;
-    *reinterpret_cast<uint4*>(out_lo + pix * C + c) = l;
-  } else {
-    const int rem = static_cast<int>(pix % (static_cast<long long>(H) * W));
-    const int y = rem / W, x = rem % W;
-    if (layout == XF_UP2) {
-      const int H2 = 2 * H, W2 = 2 * W;
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], s_scale[c + i], s_shift[c + i]);
+    }
+    if (a.silu) {
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
+      for (int i = 0; i < 16; ++i) v[i] = silu_fast(v[i]);
+    }
+    if (a.layout == XF_SAME) {
+      store_split16(v, a.out_hi + pix * C + c, a.out_lo + pix * C + c);
+    } else {
+      const int y = pl / a.W, x = pl % a.W;
+      if (a.layout == XF_UP2) {
+        const int H2 = 2 * a.H, W2 = 2 * a.W;
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const long long o = ((static_cast<long long>(b) * H2 + 2 * y + dy) * W2 + 2 * x + dx) * C + c;
-          *reinterpret_cast<uint4*>(out_hi + o) = h;
-          *reinterpret_cast<uint4*>(out_lo + o) = l;
-        }
-    } else {  // XF_S2D: [b*4 + (y&1)*2 + (x&1)][H/2][W/2][C]
-      const int Hh = H >> 1, Wh = W >> 1;
-      const long long o =
-          (((static_cast<long long>(b) * 4 + (y & 1) * 2 + (x & 1)) * Hh + (y >> 1)) * Wh + (x >> 1)) * C + c;
-      *reinterpret_cast<uint4*>(out_hi + o) = h;
-      *reinterpret_cast<uint4*>(out_lo + o) = l;
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const long long o = ((static_cast<long long>(b) * H2 + 2 * y + dy) * W2 + 2 * x + dx) * C + c;
+            store_split16(v, a.out_hi + o, a.out_lo + o);
+          }
+      } else {  // XF_S2D: [b*4 + (y&1)*2 + (x&1)][H/2][W/2][C]
+        const int Hh = a.H >> 1, Wh = a.W >> 1;
+        const long long o =
+            (((static_cast<long long>(b) * 4 + (y & 1) * 2 + (x & 1)) * Hh + (y >> 1)) * Wh + (x >> 1)) * C + c;
+        store_split16(v, a.out_hi + o, a.out_lo + o);
+      }
     }
   }
 }
 
-void launch_act_split(const float* src0, int C0, const float* src1, int C1, const float* scale,
-                      const float* shift, int silu, int layout, bf16* out_hi, bf16* out_lo, int B,
-                      int H, int W, cudaStream_t s) {
-  const long long total = static_cast<long long>(B) * H * W * ((C0 + C1) >> 3);
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  act_split_kernel<<<blocks, 256, 0, s>>>(src0, C0, src1, C1, scale, shift, silu, layout, out_hi,
-                                          out_lo, B, H, W);
+void launch_act_split(const ActSplitArgs& a, cudaStream_t s) {
+  const int C = a.C0 + a.C1;
+  const long long items = static_cast<long long>(a.H) * a.W * (C >> 4);
+  dim3 grid(static_cast<unsigned>((items + 256 * AS_IPT - 1) / (256 * AS_IPT)), a.B);
+  act_split_kernel<<<grid, 256, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -435,34 +440,45 @@ void launch_transpose_split(const float* src, bf16* hi, bf16* lo, int imgs, int 
   transpose_split_kernel<<<grid, 256, 0, s>>>(src, hi, lo, rows, C);
 }
 
-// warp per output element
+// tiled fp32 SGEMM for the per-sample vectors: block = 16 samples x 16 output columns, K in chunks
+// of 32 through smem (both operands are K-contiguous, so the tile loads are coalesced)
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in,
                                                            long long ld_in,
                                                            const float* __restrict__ W,
                                                            const float* __restrict__ bias,
                                                            float* __restrict__ out, long long ld_out,
-                                                           int B, int N, int K, int in_act) {
-  const long long o = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (o >= static_cast<long long>(B) * N) return;
-  const int lane = threadIdx.x & 31;
-  const int b = static_cast<int>(o / N), n = static_cast<int>(o % N);
-  const float* ip = in + b * ld_in;
-  const float* wp = W + static_cast<long long>(n) * K;
+                                                           int B, int N, int K, int out_act) {
+  __shared__ float s_in[16][33];
+  __shared__ float s_w[16][33];
+  const int tn = threadIdx.x & 15, tb = threadIdx.x >> 4;
+  const int n0 = blockIdx.x * 16, b0 = blockIdx.y * 16;
+  const int lr = threadIdx.x >> 5, lk = threadIdx.x & 31;  // loader: rows lr and lr + 8, column lk
   float acc = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    float v = __ldg(ip + k);
-    if (in_act) v = silu_f(v);
-    acc = fmaf(v, __ldg(wp + k), acc);
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lr + 8 * h;
+      const int k = k0 + lk;
+      s_in[r][lk] = (b0 + r < B && k < K) ? __ldg(in + (b0 + r) * ld_in + k) : 0.f;
+      s_w[r][lk] = (n0 + r < N && k < K) ? __ldg(W + static_cast<long long>(n0 + r) * K + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc = fmaf(s_in[tb][k], s_w[tn][k], acc);
+    __syncthreads();
   }
-  acc = warp_sum(acc);
-  if (lane == 0) out[b * ld_out + n] = acc + (bias ? bias[n] : 0.f);
+  const int b = b0 + tb, n = n0 + tn;
+  if (b < B && n < N) {
+    acc += bias ? bias[n] : 0.f;
+    if (out_act) acc = silu_f(acc);
+    out[b * ld_out + n] = acc;
+  }
 }
 void launch_small_linear(const float* in, long long ld_in, const float* W, const float* bias,
-                         float* out, long long ld_out, int B, int N, int K, int in_act,
+                         float* out, long long ld_out, int B, int N, int K, int out_act,
                          cudaStream_t s) {
-  const long long total = static_cast<long long>(B) * N;
-  small_linear_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, s>>>(in, ld_in, W, bias, out,
-                                                                              ld_out, B, N, K, in_act);
+  dim3 grid((N + 15) / 16, (B + 15) / 16);
+  small_linear_kernel<<<grid, 256, 0, s>>>(in, ld_in, W, bias, out, ld_out, B, N, K, out_act);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -470,8 +486,9 @@ void launch_small_linear(const float* in, long long ld_in, const float* W, const
 // ------------------------------------------------------------------------------------------------
 constexpr int CO_T = 16;
 __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__ h,
-                                                       const float* __restrict__ scale,
-                                                       const float* __restrict__ shift,
+                                                       const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps,
                                                        const float* __restrict__ w,
                                                        const float* __restrict__ bias,
                                                        float* __restrict__ out, int H, int W, int C,
@@ -480,16 +497,38 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__
   const int pitch = C + 4;
   float* st = sm;                                        // [(T+2)*(T+2)][pitch]
   float* sw = sm + (CO_T + 2) * (CO_T + 2) * pitch;      // [Cout][9][C]
+  float* sc = sw + Cout * 9 * C;                         // [C] GroupNorm scale
+  float* sh = sc + C;                                    // [C] GroupNorm shift
   const int b = blockIdx.z, ty = blockIdx.y * CO_T, tx = blockIdx.x * CO_T;
   const int c4n = C >> 2;
+  {
+    // GroupNorm(32) finalised from the producer's per-(sample, channel) fp64 sums
+    const int cpg = C / 32;
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const int g = c / cpg;
+      double ts = 0.0, tq = 0.0;
+      for (int i = 0; i < cpg; ++i) {
+        const double* a = stats + (static_cast<long long>(b) * C + g * cpg + i) * 2;
+        ts += a[0];
+        tq += a[1];
+      }
+      const double n = static_cast<double>(H) * W * cpg;
+      const double mean = ts / n;
+      double var = tq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      const float s1 = gamma[c] * rstd;
+      sc[c] = s1;
+      sh[c] = beta[c] - static_cast<float>(mean) * s1;
+    }
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < Cout * 9 * C; i += 256) {
     // w [Cout][C][3][3] -> sw[co][tap][c]
     const int co = i / (9 * C), r = i % (9 * C);
     const int tap = r / C, c = r % C;
     sw[i] = w[(static_cast<long long>(co) * C + c) * 9 + tap];
   }
-  const float* sc = scale + static_cast<long long>(b) * C;
-  const float* sh = shift + static_cast<long long>(b) * C;
   for (int i = threadIdx.x; i < (CO_T + 2) * (CO_T + 2) * c4n; i += 256) {
     const int pix = i / c4n, c = (i % c4n) * 4;
     const int gy = ty + pix / (CO_T + 2) - 1, gx = tx + pix % (CO_T + 2) - 1;
@@ -497,10 +536,10 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__
     if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(
           h + ((static_cast<long long>(b) * H + gy) * W + gx) * C + c));
-      v.x = silu_f(fmaf(a.x, sc[c + 0], sh[c + 0]));
-      v.y = silu_f(fmaf(a.y, sc[c + 1], sh[c + 1]));
-      v.z = silu_f(fmaf(a.z, sc[c + 2], sh[c + 2]));
-      v.w = silu_f(fmaf(a.w, sc[c + 3], sh[c + 3]));
+      v.x = silu_fast(fmaf(a.x, sc[c + 0], sh[c + 0]));
+      v.y = silu_fast(fmaf(a.y, sc[c + 1], sh[c + 1]));
+      v.z = silu_fast(fmaf(a.z, sc[c + 2], sh[c + 2]));
+      v.w = silu_fast(fmaf(a.w, sc[c + 3], sh[c + 3]));
     }
     *reinterpret_cast<float4*>(st + pix * pitch + c) = v;
   }
@@ -528,18 +567,18 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__
       out[((static_cast<long long>(b) * Cout + co) * H + gy) * W + gx] = acc[co] + bias[co];
 }
 
-void launch_conv_out(const float* h, const float* scale, const float* shift, const float* w,
-                     const float* bias, float* out, int B, int H, int W, int C, int Cout,
-                     cudaStream_t s) {
+void launch_conv_out(const float* h, const double* stats, const float* gamma, const float* beta,
+                     float eps, const float* w, const float* bias, float* out, int B, int H, int W,
+                     int C, int Cout, cudaStream_t s) {
   static bool attr_set = false;
-  const size_t smem =
-      (static_cast<size_t>(CO_T + 2) * (CO_T + 2) * (C + 4) + static_cast<size_t>(Cout) * 9 * C) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(CO_T + 2) * (CO_T + 2) * (C + 4) +
+                       static_cast<size_t>(Cout) * 9 * C + 2 * C) * sizeof(float);
   if (!attr_set) {
     cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   dim3 grid((W + CO_T - 1) / CO_T, (H + CO_T - 1) / CO_T, B);
-  conv_out_kernel<<<grid, 256, smem, s>>>(h, scale, shift, w, bias, out, H, W, C, Cout);
+  conv_out_kernel<<<grid, 256, smem, s>>>(h, stats, gamma, beta, eps, w, bias, out, H, W, C, Cout);
 }
 
 // ------------------------------------------------------------------------------------------------

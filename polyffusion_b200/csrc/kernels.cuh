@@ -21,16 +21,23 @@ void launch_conv_in(const float* x, const float* w, const float* bias, float* ou
 // feature map gets its statistics from the producing GEMM's epilogue)
 void launch_gn_stats(const float* src, double* acc, int B, int HW, int Cs, int Ctot, int coff,
                      cudaStream_t s);
-// acc -> scale/shift [B, Ctot] for GroupNorm(groups, eps) with affine gamma/beta
-void launch_gn_finalize(const double* acc0, int C0, const double* acc1, const float* gamma,
-                        const float* beta, float* scale, float* shift, int B, int HW, int Ctot,
-                        int groups, float eps, cudaStream_t s);
-
 enum XformLayout : int { XF_SAME = 0, XF_UP2 = 1, XF_S2D = 2 };
-// out_hi/lo[b, y', x', c] = split(act(scale*cat(src0,src1) + shift)); act = SiLU if silu.
-void launch_act_split(const float* src0, int C0, const float* src1, int C1, const float* scale,
-                      const float* shift, int silu, int layout, bf16* out_hi, bf16* out_lo, int B,
-                      int H, int W, cudaStream_t s);
+// Operand transform: out_hi/lo[b, y', x', c] = split(act(GN(cat(src0, src1)))); act = SiLU if silu.
+// GroupNorm(groups, eps, gamma, beta) is applied when stats0 != null, using the per-(sample, channel)
+// fp64 sum / sum-of-squares buffers of each source ([B][C0][2], [B][C1][2]).  out2 (optional) receives
+// the plain split of the un-normalised input.  (C0 + C1) % 16 == 0, C0 % 16 == 0, C0 + C1 <= 512.
+struct ActSplitArgs {
+  const float* src0; int C0;
+  const float* src1; int C1;
+  const double* stats0; const double* stats1;
+  const float* gamma; const float* beta;
+  float eps; int groups;
+  int silu, layout;
+  bf16* out_hi; bf16* out_lo;
+  bf16* out2_hi; bf16* out2_lo;
+  int B, H, W;
+};
+void launch_act_split(const ActSplitArgs& a, cudaStream_t s);
 
 // LayerNorm over C (eps) + affine -> split bf16 [rows, C]; C multiple of 128, <= 512
 void launch_ln_split(const float* src, const float* gamma, const float* beta, float eps,
@@ -49,15 +56,15 @@ void launch_time_sinusoid(const long long* t, const float* freqs, float* out, in
 void launch_merge_split(const bf16* hi, const bf16* lo, float* out, long long n, cudaStream_t s);
 void launch_transpose_split(const float* src, bf16* hi, bf16* lo, int imgs, int rows, int C,
                             cudaStream_t s);
-// out[b, n] = W[n,:] . act(in[b,:]) + bias[n]; in_act: 0 none, 1 SiLU.  fp32 exact-order-free.
+// out[b, n] = act(W[n,:] . in[b,:] + bias[n]); out_act: 0 none, 1 SiLU.  fp32.
 void launch_small_linear(const float* in, long long ld_in, const float* W, const float* bias,
-                         float* out, long long ld_out, int B, int N, int K, int in_act,
+                         float* out, long long ld_out, int B, int N, int K, int out_act,
                          cudaStream_t s);
 
 // GroupNorm-apply + SiLU + conv3x3 (C -> Cout small) -> NCHW out (unet.py:145-149)
-void launch_conv_out(const float* h, const float* scale, const float* shift, const float* w,
-                     const float* bias, float* out, int B, int H, int W, int C, int Cout,
-                     cudaStream_t s);
+void launch_conv_out(const float* h, const double* stats, const float* gamma, const float* beta,
+                     float eps, const float* w, const float* bias, float* out, int B, int H, int W,
+                     int C, int Cout, cudaStream_t s);
 
 // weight packing: w [Cout, Cin, kh, kw] fp32 -> split bf16 [kh*kw][Cout_total][Cin] rows at row0
 // geglu_gran > 0: interleave the [x | gate] halves of a GeGLU projection in blocks of geglu_gran rows

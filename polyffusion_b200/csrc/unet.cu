@@ -67,6 +67,7 @@ struct Op {
   int bn = 0;
   GemmParams g;
   AttnParams a;
+  ActSplitArgs as;
   const void* p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void* o[2] = {nullptr, nullptr};
   long long i[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -350,6 +351,7 @@ struct Builder {
     op.kind = k;
     memset(&op.g, 0, sizeof op.g);
     memset(&op.a, 0, sizeof op.a);
+    memset(&op.as, 0, sizeof op.as);
     return op;
   }
 
@@ -374,34 +376,39 @@ struct Builder {
     return acc;
   }
 
-  void gn_scale_shift(const T& x0, const T* x1, const std::string& gname, const std::string& bname,
-                      float eps, float*& scale, float*& shift) {
+  // split-bf16 operand of act(GN(cat(x0, x1))).  norm_prefix empty -> no normalisation.  When
+  // `plain` is given it receives the plain split of the same input (one pass, two outputs).
+  Split act_split(const T& x0, const T* x1, const std::string& norm_prefix, float eps, bool silu,
+                  int layout, Split* plain = nullptr) {
     const int C = x0.C + (x1 ? x1->C : 0);
-    const int HW = x0.H * x0.W;
-    PF_CHECK(C % 32 == 0, "GroupNorm channels %d not divisible by 32", C);
-    const double* a0 = stats_of(x0);
-    const double* a1 = x1 ? stats_of(*x1) : nullptr;
-    scale = alloc<float>(static_cast<size_t>(B) * C);
-    shift = alloc<float>(static_cast<size_t>(B) * C);
-    Op& op = push(OP_GN_FINALIZE);
-    op.p[0] = a0; op.p[1] = F(m, gname); op.p[2] = F(m, bname); op.p[3] = a1;
-    op.o[0] = scale; op.o[1] = shift;
-    op.i[0] = B; op.i[1] = HW; op.i[2] = C; op.i[3] = 32; op.i[4] = x0.C;
-    op.f = eps;
-  }
-
-  // split-bf16 operand of act(GN(cat(x0, x1)))
-  Split act_split(const T& x0, const T* x1, const float* scale, const float* shift, bool silu,
-                  int layout) {
-    const int C = x0.C + (x1 ? x1->C : 0);
+    PF_CHECK(C % 16 == 0 && x0.C % 16 == 0 && (norm_prefix.empty() || C <= 512),
+             "operand transform: unsupported channels %d+%d", x0.C, x1 ? x1->C : 0);
     size_t count = static_cast<size_t>(B) * x0.H * x0.W * C;
+    const size_t count_plain = count;
     if (layout == XF_UP2) count *= 4;
     Split s = alloc_split(count);
+    const double* st0 = nullptr;
+    const double* st1 = nullptr;
+    if (!norm_prefix.empty()) {
+      PF_CHECK(C % 32 == 0, "GroupNorm channels %d not divisible by 32", C);
+      st0 = stats_of(x0);
+      st1 = x1 ? stats_of(*x1) : nullptr;
+    }
+    if (plain) *plain = alloc_split(count_plain);
     Op& op = push(OP_ACT_SPLIT);
-    op.p[0] = x0.p; op.p[1] = x1 ? x1->p : nullptr; op.p[2] = scale; op.p[3] = shift;
-    op.o[0] = s.hi; op.o[1] = s.lo;
-    op.i[0] = x0.C; op.i[1] = x1 ? x1->C : 0; op.i[2] = silu; op.i[3] = layout;
-    op.i[4] = B; op.i[5] = x0.H; op.i[6] = x0.W;
+    ActSplitArgs& a = op.as;
+    a.src0 = x0.p; a.C0 = x0.C;
+    a.src1 = x1 ? x1->p : nullptr; a.C1 = x1 ? x1->C : 0;
+    a.stats0 = st0; a.stats1 = st1;
+    if (!norm_prefix.empty()) {
+      a.gamma = F(m, norm_prefix + ".weight");
+      a.beta = F(m, norm_prefix + ".bias");
+    }
+    a.eps = eps; a.groups = 32;
+    a.silu = silu; a.layout = layout;
+    a.out_hi = s.hi; a.out_lo = s.lo;
+    a.out2_hi = plain ? plain->hi : nullptr; a.out2_lo = plain ? plain->lo : nullptr;
+    a.B = B; a.H = x0.H; a.W = x0.W;
     return s;
   }
 
@@ -417,12 +424,12 @@ struct Builder {
   }
 
   void small_linear(const float* in, long long ld_in, const float* Wt, const float* bias, float* out,
-                    long long ld_out, int N, int K, int in_act, int ext = EXT_NONE) {
+                    long long ld_out, int N, int K, int out_act, int ext = EXT_NONE) {
     Op& op = push(OP_SMALL_LINEAR);
     op.ext = ext;
     op.p[0] = in; op.p[1] = Wt; op.p[2] = bias;
     op.o[0] = out;
-    op.i[0] = ld_in; op.i[1] = ld_out; op.i[2] = B; op.i[3] = N; op.i[4] = K; op.i[5] = in_act;
+    op.i[0] = ld_in; op.i[1] = ld_out; op.i[2] = B; op.i[3] = N; op.i[4] = K; op.i[5] = out_act;
   }
 
   // ---------------------------------------------------------------- GEMM emitters
@@ -501,11 +508,9 @@ struct Builder {
     PF_CHECK(C == L.cin, "ResBlock %s: got %d input channels, expected %d", L.name.c_str(), C, L.cin);
     const int H = x0.H, Wd = x0.W;
     const size_t npix = static_cast<size_t>(B) * H * Wd;
-    float *sc, *sh;
-    gn_scale_shift(x0, x1, L.name + ".in_layers.0.weight", L.name + ".in_layers.0.bias", 1e-5f, sc, sh);
-    Split a1 = act_split(x0, x1, sc, sh, true, XF_SAME);
-    arena.free(sc);
-    arena.free(sh);
+    Split a3;  // plain split of the input for the 1x1 skip conv (same pass as the normalised one)
+    Split a1 = act_split(x0, x1, L.name + ".in_layers.0", 1e-5f, true, XF_SAME,
+                         L.cin != L.cout ? &a3 : nullptr);
     T h1;
     h1.C = L.cout; h1.H = H; h1.W = Wd;
     h1.p = alloc<float>(npix * L.cout);
@@ -518,10 +523,7 @@ struct Builder {
       out_f32(op, h1.p, L.cout, emb_all + L.emb_off, m->emb_total, nullptr, 0, h1.stats);
     }
     free_split(a1);
-    gn_scale_shift(h1, nullptr, L.name + ".out_layers.0.weight", L.name + ".out_layers.0.bias", 1e-5f, sc, sh);
-    Split a2 = act_split(h1, nullptr, sc, sh, true, XF_SAME);
-    arena.free(sc);
-    arena.free(sh);
+    Split a2 = act_split(h1, nullptr, L.name + ".out_layers.0", 1e-5f, true, XF_SAME);
     arena.free(h1.p);
     T y;
     y.C = L.cout; y.H = H; y.W = Wd;
@@ -530,7 +532,6 @@ struct Builder {
     PackedW& w2 = W(m, L.name + ".out_layers.3.weight", {L.name + ".out_layers.3.weight"});
     ASrc s2{a2, L.cout, Wd, H, B, 1};
     if (L.cin != L.cout) {
-      Split a3 = act_split(x0, x1, nullptr, nullptr, false, XF_SAME);
       PackedW& ws = W(m, L.name + ".skip_connection.weight", {L.name + ".skip_connection.weight"});
       ASrc s3{a3, C, Wd, H, B, 0};
       Op& op = conv_gemm(s2, w2, &s3, &ws, H, Wd, L.cout);
@@ -669,11 +670,7 @@ struct Builder {
     PF_CHECK(N % 128 == 0, "SpatialTransformer: %d tokens per image is not a multiple of 128", N);
     const long long rows = static_cast<long long>(B) * N;
     const int sti = st_index++;
-    float *sc, *sh;
-    gn_scale_shift(x, nullptr, L.name + ".norm.weight", L.name + ".norm.bias", 1e-6f, sc, sh);
-    Split a = act_split(x, nullptr, sc, sh, false, XF_SAME);
-    arena.free(sc);
-    arena.free(sh);
+    Split a = act_split(x, nullptr, L.name + ".norm", 1e-6f, false, XF_SAME);
     float* t0 = alloc<float>(rows * C);
     {
       PackedW& w = W(m, L.name + ".proj_in.weight", {L.name + ".proj_in.weight"});
@@ -761,7 +758,7 @@ struct Builder {
         T ct;
         ct.p = const_cast<float*>(cond_ext);
         ct.C = c.d_cond; ct.H = 1; ct.W = n_cond;
-        Split cs = act_split(ct, nullptr, nullptr, nullptr, false, XF_SAME);
+        Split cs = act_split(ct, nullptr, "", 0.f, false, XF_SAME);
         plan->ops.back().ext = EXT_COND;
         const long long crow = static_cast<long long>(B) * n_cond;
         Split k2 = alloc_split(crow * C);
@@ -824,7 +821,7 @@ struct Builder {
     // proj_out + residual
     T tt;
     tt.p = t0; tt.C = C; tt.H = H; tt.W = Wd;
-    Split ao = act_split(tt, nullptr, nullptr, nullptr, false, XF_SAME);
+    Split ao = act_split(tt, nullptr, "", 0.f, false, XF_SAME);
     arena.free(t0);
     T y;
     y.C = C; y.H = H; y.W = Wd;
@@ -842,7 +839,7 @@ struct Builder {
 
   T down_sample(const Layer& L, const T& x) {
     PF_CHECK(x.H % 2 == 0 && x.W % 2 == 0, "DownSample needs even dims");
-    Split a = act_split(x, nullptr, nullptr, nullptr, false, XF_S2D);
+    Split a = act_split(x, nullptr, "", 0.f, false, XF_S2D);
     T y;
     y.C = x.C; y.H = x.H / 2; y.W = x.W / 2;
     y.p = alloc<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
@@ -856,7 +853,7 @@ struct Builder {
   }
 
   T up_sample(const Layer& L, const T& x) {
-    Split a = act_split(x, nullptr, nullptr, nullptr, false, XF_UP2);
+    Split a = act_split(x, nullptr, "", 0.f, false, XF_UP2);
     T y;
     y.C = x.C; y.H = x.H * 2; y.W = x.W * 2;
     y.p = alloc<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
@@ -902,8 +899,10 @@ struct Builder {
     }
     float* te1 = alloc<float>(static_cast<size_t>(B) * d_temb);
     float* temb = alloc<float>(static_cast<size_t>(B) * d_temb);
+    // te1 = SiLU(Linear(sinusoid)); temb = SiLU(Linear(te1)): every consumer of t_emb applies SiLU
+    // first (ResBlock.emb_layers, unet.py:286-289), so the activated value is what gets stored
     small_linear(sinus, c.channels, F(m, "time_embed.0.weight"), F(m, "time_embed.0.bias"), te1,
-                 d_temb, d_temb, c.channels, 0);
+                 d_temb, d_temb, c.channels, 1);
     small_linear(te1, d_temb, F(m, "time_embed.2.weight"), F(m, "time_embed.2.bias"), temb, d_temb,
                  d_temb, d_temb, 1);
     {
@@ -922,7 +921,7 @@ struct Builder {
       const float* wcat = Fcat(m, "emb_all.weight", wn, nullptr);
       const float* bcat = Fcat(m, "emb_all.bias", bn_, &cb);
       float* ea = alloc<float>(static_cast<size_t>(B) * m->emb_total);
-      small_linear(temb, d_temb, wcat, bcat, ea, m->emb_total, m->emb_total, d_temb, 1);
+      small_linear(temb, d_temb, wcat, bcat, ea, m->emb_total, m->emb_total, d_temb, 0);
       emb_all = ea;
     }
     // ---- cross-attention value vectors for n_cond == 1
@@ -1002,12 +1001,14 @@ struct Builder {
     }
     // ---- out: GroupNorm + SiLU + conv3x3 -> NCHW (unet.py:145-149, 196)
     {
-      float *sc, *sh;
-      gn_scale_shift(x, nullptr, "out.0.weight", "out.0.bias", 1e-5f, sc, sh);
       PF_CHECK(c.out_channels <= 4, "out_channels > 4 unsupported by the final conv kernel");
+      PF_CHECK(x.C % 32 == 0, "final GroupNorm: channels %d not divisible by 32", x.C);
+      const double* st = stats_of(x);
       Op& op = push(OP_CONV_OUT);
       op.ext = EXT_OUT;
-      op.p[0] = x.p; op.p[1] = sc; op.p[2] = sh; op.p[3] = F(m, "out.2.weight"); op.p[4] = F(m, "out.2.bias");
+      op.p[0] = x.p; op.p[1] = st; op.p[2] = F(m, "out.0.weight"); op.p[3] = F(m, "out.2.weight");
+      op.p[4] = F(m, "out.2.bias"); op.p[5] = F(m, "out.0.bias");
+      op.f = 1e-5f;
       op.i[0] = B; op.i[1] = H; op.i[2] = Wd; op.i[3] = x.C; op.i[4] = c.out_channels;
     }
   }
@@ -1039,19 +1040,13 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
                         (int)op.i[1], (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
         break;
       case OP_GN_FINALIZE:
-        launch_gn_finalize(static_cast<const double*>(op.p[0]), (int)op.i[4],
-                           static_cast<const double*>(op.p[3]), static_cast<const float*>(op.p[1]),
-                           static_cast<const float*>(op.p[2]), static_cast<float*>(op.o[0]),
-                           static_cast<float*>(op.o[1]), (int)op.i[0], (int)op.i[1], (int)op.i[2],
-                           (int)op.i[3], op.f, s);
+        break;  // (retired: GroupNorm is finalised inside the operand transform / final conv)
+      case OP_ACT_SPLIT: {
+        ActSplitArgs a = op.as;
+        if (op.ext == EXT_COND) a.src0 = cond;
+        launch_act_split(a, s);
         break;
-      case OP_ACT_SPLIT:
-        launch_act_split(op.ext == EXT_COND ? cond : static_cast<const float*>(op.p[0]), (int)op.i[0],
-                         static_cast<const float*>(op.p[1]), (int)op.i[1],
-                         static_cast<const float*>(op.p[2]), static_cast<const float*>(op.p[3]),
-                         (int)op.i[2], (int)op.i[3], static_cast<bf16*>(op.o[0]),
-                         static_cast<bf16*>(op.o[1]), (int)op.i[4], (int)op.i[5], (int)op.i[6], s);
-        break;
+      }
       case OP_LN_SPLIT:
         launch_ln_split(static_cast<const float*>(op.p[0]), static_cast<const float*>(op.p[1]),
                         static_cast<const float*>(op.p[2]), op.f, static_cast<bf16*>(op.o[0]),
@@ -1076,10 +1071,10 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
                             (int)op.i[4], (int)op.i[5], s);
         break;
       case OP_CONV_OUT:
-        launch_conv_out(static_cast<const float*>(op.p[0]), static_cast<const float*>(op.p[1]),
-                        static_cast<const float*>(op.p[2]), static_cast<const float*>(op.p[3]),
-                        static_cast<const float*>(op.p[4]), out, (int)op.i[0], (int)op.i[1],
-                        (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
+        launch_conv_out(static_cast<const float*>(op.p[0]), static_cast<const double*>(op.p[1]),
+                        static_cast<const float*>(op.p[2]), static_cast<const float*>(op.p[5]), op.f,
+                        static_cast<const float*>(op.p[3]), static_cast<const float*>(op.p[4]), out,
+                        (int)op.i[0], (int)op.i[1], (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
         break;
     }
   }
@@ -1293,6 +1288,10 @@ int pf_unet_op_desc(pf_unet* h, int32_t i, char* buf, int32_t len) {
       snprintf(buf, len, "gemm M=%lld N=%d K=%d bn=%d taps=%d nseg=%d z=%d mode=%d stages=%d",
                static_cast<long long>(g.m_tiles) * 128, g.n_tiles * op.bn, k, op.bn, g.seg[0].ntaps,
                g.nseg, g.z_count, g.mode, g.nstages);
+    } else if (op.kind == OP_ACT_SPLIT) {
+      snprintf(buf, len, "act_split C=%d+%d HxW=%dx%d B=%d norm=%d silu=%d layout=%d dual=%d", op.as.C0,
+               op.as.C1, op.as.H, op.as.W, op.as.B, op.as.stats0 != nullptr, op.as.silu, op.as.layout,
+               op.as.out2_hi != nullptr);
     } else if (op.kind == OP_ATTN) {
       snprintf(buf, len, "attn B=%d heads=%d N=%d Nk=%d", op.a.B, op.a.heads, op.a.N, op.a.Nk);
     } else {
@@ -1406,7 +1405,7 @@ int pf_op_conv2d_nhwc(const float* x, int32_t B, int32_t H, int32_t W_, int32_t 
     T xt;
     xt.p = const_cast<float*>(x); xt.C = Cin; xt.H = H; xt.W = W_;
     const int layout = upsample ? XF_UP2 : (stride == 2 ? XF_S2D : XF_SAME);
-    Split a = b.act_split(xt, nullptr, nullptr, nullptr, false, layout);
+    Split a = b.act_split(xt, nullptr, "", 0.f, false, layout);
     const int Ho = upsample ? 2 * H : H / stride, Wo = upsample ? 2 * W_ : W_ / stride;
     Builder::ASrc src{a, Cin, Wo, Ho, stride == 2 ? 4 * B : B, ksize == 1 ? 0 : (stride == 2 ? 2 : 1)};
     PackedW& pw = W(&tm.m, "w", {"w"});
@@ -1443,8 +1442,8 @@ int pf_op_attention(const float* q, const float* k, const float* v, int32_t B, i
     T qt, kt;
     qt.p = const_cast<float*>(q); qt.C = C; qt.H = 1; qt.W = N;
     kt.p = const_cast<float*>(k); kt.C = C; kt.H = 1; kt.W = Nk;
-    Split qs = b.act_split(qt, nullptr, nullptr, nullptr, false, XF_SAME);
-    Split ks = b.act_split(kt, nullptr, nullptr, nullptr, false, XF_SAME);
+    Split qs = b.act_split(qt, nullptr, "", 0.f, false, XF_SAME);
+    Split ks = b.act_split(kt, nullptr, "", 0.f, false, XF_SAME);
     Split vt = b.alloc_split(static_cast<size_t>(B) * Nk * C);
     Split o = b.alloc_split(static_cast<size_t>(B) * N * C);
     run_plan(&tm.m, plan, nullptr, nullptr, nullptr, nullptr, s);
@@ -1464,8 +1463,8 @@ int pf_op_groupnorm_nhwc(const float* x, int32_t B, int32_t HW, int32_t C, const
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TempModel tm;
     tm.m.pack_stream = s;
-    tm.set("g", gamma, {C});
-    tm.set("b", beta, {C});
+    tm.set("gn.weight", gamma, {C});
+    tm.set("gn.bias", beta, {C});
     const size_t ws_bytes = static_cast<size_t>(B) * HW * C * 4 + static_cast<size_t>(B) * C * 32 + (1 << 20);
     PF_CUDA(cudaMalloc(&tm.ws, ws_bytes));
     Plan plan;
@@ -1475,9 +1474,7 @@ int pf_op_groupnorm_nhwc(const float* x, int32_t B, int32_t HW, int32_t C, const
     PF_CUDA(cudaMemsetAsync(b.gn_pool, 0, b.gn_pool_doubles * sizeof(double), s));
     T xt;
     xt.p = const_cast<float*>(x); xt.C = C; xt.H = 1; xt.W = HW;
-    float *sc, *sh;
-    b.gn_scale_shift(xt, nullptr, "g", "b", eps, sc, sh);
-    Split a = b.act_split(xt, nullptr, sc, sh, silu != 0, XF_SAME);
+    Split a = b.act_split(xt, nullptr, "gn", eps, silu != 0, XF_SAME);
     run_plan(&tm.m, plan, nullptr, nullptr, nullptr, nullptr, s);
     launch_merge_split(a.hi, a.lo, out, static_cast<long long>(B) * HW * C, s);
     PF_CUDA(cudaStreamSynchronize(s));
