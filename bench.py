@@ -262,19 +262,24 @@ def run_gpu_arm(args):
     # ---- per-kernel breakdown of one step (CUDA events around every launch of the plan)
     prof = {}
     ts = x.new_full((B,), 500, dtype=torch.long)
-    gemm_ms, gemm_flops, other_ms, gemm_launches = 0.0, 0.0, 0.0, 0
+    gemm_ms, gemm_flops, other_ms, gemm_launches, attn_ms, attn_flops = 0.0, 0.0, 0.0, 0, 0.0, 0.0
     n_prof = 3
     for _ in range(n_prof):
         unet.engine.forward(x, ts, cond, profile=prof)
         for ms, fl, kd in zip(prof["ms"], prof["flops"], prof["kind"]):
-            if kd == 0:
+            if kd == 0:  # gemm_tc_kernel
                 gemm_ms += ms
                 gemm_flops += fl
                 gemm_launches += 1
+            elif kd == 12:  # attn_tc_kernel
+                attn_ms += ms
+                attn_flops += fl
             else:
                 other_ms += ms
     gemm_ms /= n_prof
     gemm_flops /= n_prof
+    attn_ms /= n_prof
+    attn_flops /= n_prof
     other_ms /= n_prof
     gemm_launches //= n_prof
 
@@ -305,7 +310,9 @@ def run_gpu_arm(args):
                 "unet_algorithmic_tflops": GFLOP_PER_SAMPLE_EVAL * B / 1e3 / (ms_per_step / 1e3),
                 "precision_note": "3 tcgen05 MMAs per algorithmic product (hi*hi + lo*hi + hi*lo): "
                                   "algorithmic FLOP/s is capped at 1/3 of issued tensor FLOP/s",
-                "step_breakdown_ms": {"tcgen05_gemm": gemm_ms, "other_kernels": other_ms},
+                "step_breakdown_ms": {"tcgen05_gemm": gemm_ms, "tcgen05_attention": attn_ms,
+                                      "other_kernels": other_ms},
+                "attention_algorithmic_tflops": (attn_flops / (attn_ms * 1e-3) / 1e12) if attn_ms > 0 else None,
             },
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": UNIT,
