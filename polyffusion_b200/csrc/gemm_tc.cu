@@ -18,12 +18,17 @@ struct TileCoord {
   int n0, tile, zb, zh, img, trem, x0, y0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, long long t, int bn) {
+// pair_rank < 0: t indexes single tiles; otherwise t indexes tile pairs and the CTA takes m-tile
+// 2 * pair + pair_rank
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, long long t, int bn,
+                                                 int pair_rank = -1) {
   TileCoord c;
   const int nt = static_cast<int>(t % p.n_tiles);
   const long long r = t / p.n_tiles;
-  c.tile = static_cast<int>(r % p.m_tiles);
-  const int z = static_cast<int>(r / p.m_tiles);
+  const int mt = pair_rank < 0 ? p.m_tiles : p.m_tiles / 2;
+  c.tile = static_cast<int>(r % mt);
+  const int z = static_cast<int>(r / mt);
+  if (pair_rank >= 0) c.tile = c.tile * 2 + pair_rank;
   c.n0 = nt * bn;
   c.zb = z / p.zdiv;
   c.zh = z % p.zdiv;
@@ -34,9 +39,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, long long 
   return c;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+// TWO = cta_group::2: a cluster of two CTAs computes a 256 x BN tile pair; each CTA stages its own
+// 128 A rows and HALF of the B rows (the MMA reads the other half from the peer's smem), so a stage
+// is 32 KB + BN*128 B instead of 32 KB + BN*256 B: more k-blocks in flight per SM and 1/3 fewer
+// operand bytes through L2.  Only the leader CTA issues MMAs; both run the epilogue on their rows.
+template <int BN, bool TWO>
+__device__ __forceinline__ void gemm_body(const GemmParams& p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -45,16 +53,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __shared__ uint32_t tmem_base_s;
 
   constexpr int A_BYTES = GEMM_BM * 128;
-  constexpr int B_BYTES = BN * 128;
+  constexpr int B_BYTES = (TWO ? BN / 2 : BN) * 128;  // B rows staged by this CTA
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  constexpr uint32_t IDESC = umma_idesc_bf16(BN);
+  constexpr uint32_t IDESC = TWO ? umma_idesc_bf16_m256(BN) : umma_idesc_bf16(BN);
   constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: power of two >= 32
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+  // tile walk: 1-CTA: tile t of this CTA; 2-CTA: pair-tile t of this cluster, my m-tile = 2*pair + rank
+  const long long wid = TWO ? (blockIdx.x >> 1) : blockIdx.x;
+  const long long wstride = TWO ? (gridDim.x >> 1) : gridDim.x;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nstages = p.nstages;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const long long total_tiles = static_cast<long long>(p.n_tiles) * p.m_tiles * p.z_count;
+  const long long total_tiles =
+      static_cast<long long>(p.n_tiles) * (TWO ? p.m_tiles / 2 : p.m_tiles) * p.z_count;
 
   int nkb = 0;
   for (int s = 0; s < p.nseg; ++s) nkb += p.seg[s].ntaps * p.seg[s].kb_per_tap;
@@ -66,7 +80,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), 8);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[i]), TWO ? 16 : 8);  // one arrive per epilogue warp (both CTAs)
     }
     mbar_fence_init();
   }
@@ -79,11 +93,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_base_s), TMEM_COLS);
-    tmem_relinquish();
+    if (TWO) {
+      tmem_alloc2(smem_u32(&tmem_base_s), TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(smem_u32(&tmem_base_s), TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -91,13 +110,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int it = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t, BN);
+      for (long long t = wid; t < total_tiles; t += wstride) {
+        const TileCoord tc = decode_tile(p, t, BN, TWO ? static_cast<int>(rank) : -1);
         for (int s = 0; s < p.nseg; ++s) {
           const GemmSeg& sg = p.seg[s];
           const int acol = sg.a_col0 + tc.zb * sg.a_col_zb + tc.zh * sg.a_col_zh;
           const int aimg = (tc.img + tc.zb * sg.a_img_zb + tc.zh * sg.a_img_zh) * sg.img_mul;
-          const int brow = sg.b_row0 + tc.zb * sg.b_row_zb + tc.zh * sg.b_row_zh + tc.n0;
+          const int brow = sg.b_row0 + tc.zb * sg.b_row_zb + tc.zh * sg.b_row_zh + tc.n0 +
+                           (TWO ? static_cast<int>(rank) * (BN / 2) : 0);
           const int bcol = sg.b_col0 + tc.zb * sg.b_col_zb + tc.zh * sg.b_col_zh;
           for (int tp = 0; tp < sg.ntaps; ++tp) {
             const int ax = tc.x0 + sg.tap_dx[tp], ay = tc.y0 + sg.tap_dy[tp];
@@ -108,23 +128,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               const uint32_t ph = static_cast<uint32_t>(it / nstages) & 1u;
               mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1u);
               const uint32_t fb = smem_u32(&full_bar[stage]);
-              mbar_expect_tx(fb, STAGE_BYTES);
               const uint32_t sa = ring + stage * STAGE_BYTES;
-              tma_load_4d(sa, &sg.a_hi, fb, acol + kb * GEMM_BK, ax, ay, ai);
-              tma_load_4d(sa + A_BYTES, &sg.a_lo, fb, acol + kb * GEMM_BK, ax, ay, ai);
-              tma_load_2d(sa + 2 * A_BYTES, &sg.b_hi, fb, bcol + kb * GEMM_BK, br);
-              tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &sg.b_lo, fb, bcol + kb * GEMM_BK, br);
+              if (TWO) {
+                // both CTAs' loads complete on the LEADER's barrier, which expects both halves
+                if (leader) mbar_expect_tx(fb, 2 * STAGE_BYTES);
+                tma2_load_4d(sa, &sg.a_hi, fb, acol + kb * GEMM_BK, ax, ay, ai);
+                tma2_load_4d(sa + A_BYTES, &sg.a_lo, fb, acol + kb * GEMM_BK, ax, ay, ai);
+                tma2_load_2d(sa + 2 * A_BYTES, &sg.b_hi, fb, bcol + kb * GEMM_BK, br);
+                tma2_load_2d(sa + 2 * A_BYTES + B_BYTES, &sg.b_lo, fb, bcol + kb * GEMM_BK, br);
+              } else {
+                mbar_expect_tx(fb, STAGE_BYTES);
+                tma_load_4d(sa, &sg.a_hi, fb, acol + kb * GEMM_BK, ax, ay, ai);
+                tma_load_4d(sa + A_BYTES, &sg.a_lo, fb, acol + kb * GEMM_BK, ax, ay, ai);
+                tma_load_2d(sa + 2 * A_BYTES, &sg.b_hi, fb, bcol + kb * GEMM_BK, br);
+                tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &sg.b_lo, fb, bcol + kb * GEMM_BK, br);
+              }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && elect_one()) {
       int it = 0;
       int lt = 0;  // local tile counter
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      for (long long t = wid; t < total_tiles; t += wstride, ++lt) {
         const int as = lt & 1;
         const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1u);
@@ -143,13 +172,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t ko = static_cast<uint64_t>(k * 2);  // 32 B per K=16 step (16 B units)
-            umma_bf16(acc, da_lo + ko, db_hi + ko, IDESC, (kbi | k) != 0);
-            umma_bf16(acc, da_hi + ko, db_lo + ko, IDESC, 1u);
-            umma_bf16(acc, da_hi + ko, db_hi + ko, IDESC, 1u);
+            if (TWO) {
+              umma2_bf16(acc, da_lo + ko, db_hi + ko, IDESC, (kbi | k) != 0);
+              umma2_bf16(acc, da_hi + ko, db_lo + ko, IDESC, 1u);
+              umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC, 1u);
+            } else {
+              umma_bf16(acc, da_lo + ko, db_hi + ko, IDESC, (kbi | k) != 0);
+              umma_bf16(acc, da_hi + ko, db_lo + ko, IDESC, 1u);
+              umma_bf16(acc, da_hi + ko, db_hi + ko, IDESC, 1u);
+            }
           }
-          umma_commit(smem_u32(&empty_bar[stage]));
+          if (TWO) umma2_commit_mc(smem_u32(&empty_bar[stage]));
+          else umma_commit(smem_u32(&empty_bar[stage]));
         }
-        umma_commit(smem_u32(&tmem_full_bar[as]));
+        if (TWO) umma2_commit_mc(smem_u32(&tmem_full_bar[as]));
+        else umma_commit(smem_u32(&tmem_full_bar[as]));
       }
     }
   } else {
@@ -170,8 +207,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int et = threadIdx.x - 64;   // 0..255 among epilogue threads
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     int lt = 0;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-      const TileCoord tc = decode_tile(p, t, BN);
+    for (long long t = wid; t < total_tiles; t += wstride, ++lt) {
+      const TileCoord tc = decode_tile(p, t, BN, TWO ? static_cast<int>(rank) : -1);
       const int as = lt & 1;
       const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
       const long long m0 = static_cast<long long>(tc.tile) * GEMM_BM + q * 32;  // first row of this warp
@@ -321,7 +358,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       // all of this warp's TMEM reads for the tile are complete (tmem_ld_wait above)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+      if (lane == 0) {
+        if (TWO) mbar_arrive_leader(smem_u32(&tmem_empty_bar[as]));
+        else mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+      }
       if (p.stats) {
         // flush this tile's column sums: [img][stats_ld][2] fp64
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -345,11 +385,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (TWO) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, false>(p);
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, true>(p);
 }
 
 cudaError_t gemm_init_attrs() {
@@ -359,10 +411,29 @@ cudaError_t gemm_init_attrs() {
   e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   return e;
 }
 
 cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t stream) {
+  if (p.two_cta) {
+    const int smem = p.nstages * gemm_stage_bytes2(bn) + 1024 + gemm_epilogue_smem_bytes(bn);
+    const long long pairs = static_cast<long long>(p.n_tiles) * (p.m_tiles / 2) * p.z_count;
+    const long long max_clusters = num_ctas / 2;
+    const unsigned grid = 2u * static_cast<unsigned>(pairs < max_clusters ? pairs : max_clusters);
+    switch (bn) {
+      case 64: gemm_tc2_kernel<64><<<grid, GEMM_THREADS, smem, stream>>>(p); break;
+      case 128: gemm_tc2_kernel<128><<<grid, GEMM_THREADS, smem, stream>>>(p); break;
+      case 256: gemm_tc2_kernel<256><<<grid, GEMM_THREADS, smem, stream>>>(p); break;
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
   const int smem = gemm_smem_bytes(bn, p.nstages) + gemm_epilogue_smem_bytes(bn);
   const long long total = static_cast<long long>(p.n_tiles) * p.m_tiles * p.z_count;
   const unsigned grid = static_cast<unsigned>(total < num_ctas ? total : num_ctas);

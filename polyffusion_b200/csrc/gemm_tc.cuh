@@ -62,11 +62,14 @@ struct alignas(64) GemmParams {
   double* stats;        // OUT_F32 only: per-(image, column) sum / sum-of-squares [img][stats_ld][2]
   long long stats_ld;
   int geglu_f;          // OUT_GEGLU: number of output features F (bias layout [x: F | gate: F])
+  int two_cta;          // 1: cta_group::2 kernel (tile pairs; B maps have boxes of BN/2 rows)
 };
 
 // smem bytes for a given BN / stage count (incl. 1 KB alignment slack)
 inline int gemm_stage_bytes(int bn) { return 2 * GEMM_BM * 128 + 2 * bn * 128; }
 inline int gemm_smem_bytes(int bn, int nstages) { return nstages * gemm_stage_bytes(bn) + 1024; }
+// cta_group::2: each CTA stages its 128 A rows and half of the B rows
+inline int gemm_stage_bytes2(int bn) { return 2 * GEMM_BM * 128 + bn * 128; }
 // epilogue staging: 8 warps x (32 rows x 32 fp32)
 inline int gemm_epilogue_smem_bytes(int /*bn*/) { return 8 * 32 * 32 * 4; }
 

@@ -151,6 +151,15 @@ int gemm_default_stages(int bn) {
   return st;
 }
 
+int gemm_default_stages2(int bn) {
+  // cta_group::2 stage = 32 KB (A) + bn * 128 B (half of B); 32 KB epilogue staging + 1 KB slack
+  int st = (226 * 1024 - 1024 - 32768) / gemm_stage_bytes2(bn);
+  const int cap = env_int("PF_GEMM_MAX_STAGES", 6);
+  if (st > cap) st = cap;
+  if (st < 1) st = 1;
+  return st;
+}
+
 int choose_bn(int n) {
   static const int max_bn = env_int("PF_GEMM_MAX_BN", 256);
   if (n % 256 == 0 && max_bn >= 256) return 256;

@@ -78,6 +78,7 @@ void fill_taps_3x3_s2d(GemmSeg& sg);  // stride-2 conv over the 4 parity planes 
 void fill_taps_1x1(GemmSeg& sg);
 
 int gemm_default_stages(int bn);
+int gemm_default_stages2(int bn);  // cta_group::2 variant
 int choose_bn(int n);
 
 }  // namespace pf

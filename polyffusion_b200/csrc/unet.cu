@@ -440,7 +440,7 @@ struct Builder {
     int kind;     // 0 = 1x1 (no shift), 1 = 3x3, 2 = 3x3 stride-2 over S2D planes
   };
 
-  void fill_seg(GemmSeg& sg, const ASrc& a, PackedW& w, int bn, int box_w, int box_h) {
+  void fill_seg(GemmSeg& sg, const ASrc& a, PackedW& w, int b_box_rows, int box_w, int box_h) {
     memset(&sg, 0, sizeof sg);
     if (a.kind == 0) fill_taps_1x1(sg);
     else if (a.kind == 1) fill_taps_3x3(sg);
@@ -452,7 +452,7 @@ struct Builder {
     if (!dry) {
       sg.a_hi = make_map_4d(a.buf.hi, a.C, a.W, a.H, a.N, box_w, box_h);
       sg.a_lo = make_map_4d(a.buf.lo, a.C, a.W, a.H, a.N, box_w, box_h);
-      auto& mp = wmaps(w, bn, dry);
+      auto& mp = wmaps(w, b_box_rows, dry);
       sg.b_hi = mp.first;
       sg.b_lo = mp.second;
     }
@@ -470,16 +470,20 @@ struct Builder {
     Op& op = push(OP_GEMM);
     op.bn = bn;
     GemmParams& g = op.g;
-    fill_seg(g.seg[0], a0, w0, bn, box_w, box_h);
+    g.tiles_x = Wo / box_w;
+    g.tiles_per_img = g.tiles_x * (Ho / box_h);
+    // cta_group::2 (CTA pairs, 256-row tile pairs) whenever the M tiles pair up
+    static const bool one_cta = std::getenv("PF_GEMM_1CTA") != nullptr;
+    const bool two = !one_cta && ((B * g.tiles_per_img) % 2 == 0);
+    g.two_cta = two ? 1 : 0;
+    fill_seg(g.seg[0], a0, w0, two ? bn / 2 : bn, box_w, box_h);
     g.seg[0].b_row0 = row0;
     g.nseg = 1;
     if (a1) {
-      fill_seg(g.seg[1], *a1, *w1, bn, box_w, box_h);
+      fill_seg(g.seg[1], *a1, *w1, two ? bn / 2 : bn, box_w, box_h);
       g.nseg = 2;
     }
-    g.nstages = gemm_default_stages(bn);
-    g.tiles_x = Wo / box_w;
-    g.tiles_per_img = g.tiles_x * (Ho / box_h);
+    g.nstages = two ? gemm_default_stages2(bn) : gemm_default_stages(bn);
     g.box_w = box_w;
     g.box_h = box_h;
     g.zdiv = 1;
@@ -1285,9 +1289,9 @@ int pf_unet_op_desc(pf_unet* h, int32_t i, char* buf, int32_t len) {
       const GemmParams& g = op.g;
       int k = 0;
       for (int s = 0; s < g.nseg; ++s) k += g.seg[s].ntaps * g.seg[s].kb_per_tap * 64;
-      snprintf(buf, len, "gemm M=%lld N=%d K=%d bn=%d taps=%d nseg=%d z=%d mode=%d stages=%d",
+      snprintf(buf, len, "gemm M=%lld N=%d K=%d bn=%d taps=%d nseg=%d z=%d mode=%d stages=%d cta%d",
                static_cast<long long>(g.m_tiles) * 128, g.n_tiles * op.bn, k, op.bn, g.seg[0].ntaps,
-               g.nseg, g.z_count, g.mode, g.nstages);
+               g.nseg, g.z_count, g.mode, g.nstages, g.two_cta ? 2 : 1);
     } else if (op.kind == OP_ACT_SPLIT) {
       snprintf(buf, len, "act_split C=%d+%d HxW=%dx%d B=%d norm=%d silu=%d layout=%d dual=%d", op.as.C0,
                op.as.C1, op.as.H, op.as.W, op.as.B, op.as.stats0 != nullptr, op.as.silu, op.as.layout,
@@ -1414,8 +1418,8 @@ int pf_op_conv2d_nhwc(const float* x, int32_t B, int32_t H, int32_t W_, int32_t 
       PF_CHECK(Cout % force_bn == 0, "force_bn does not divide Cout");
       op.bn = force_bn;
       op.g.n_tiles = Cout / force_bn;
-      op.g.nstages = gemm_default_stages(force_bn);
-      auto& mp = wmaps(pw, force_bn, false);
+      op.g.nstages = op.g.two_cta ? gemm_default_stages2(force_bn) : gemm_default_stages(force_bn);
+      auto& mp = wmaps(pw, op.g.two_cta ? force_bn / 2 : force_bn, false);
       op.g.seg[0].b_hi = mp.first;
       op.g.seg[0].b_lo = mp.second;
     }
