@@ -310,7 +310,14 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           for (int it = 0; it < 8; ++it) {
             const int row = it * 4 + rsub;
             float4 o = *reinterpret_cast<const float4*>(stg + row * 32 + (((lane & 7) ^ (row & 7)) << 2));
-            const long long m = m0 + row;
+            long long m = m0 + row;
+            if (p.up_mode) {
+              // low-res pixel (y, x) of image img -> high-res pixel (2y + py, 2x + px)
+              const int r = q * 32 + row;
+              const int y = tc.y0 + r / p.box_w, x = tc.x0 + r % p.box_w;
+              const int Wl = p.tiles_x * p.box_w, Hl = (p.tiles_per_img / p.tiles_x) * p.box_h;
+              m = (static_cast<long long>(tc.img) * (2 * Hl) + 2 * y + p.up_py) * (2 * Wl) + 2 * x + p.up_px;
+            }
             if (p.mode == OUT_F32) {
               if (has_res) {
                 o.x += rres[it].x; o.y += rres[it].y; o.z += rres[it].z; o.w += rres[it].w;

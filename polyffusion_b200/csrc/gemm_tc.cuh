@@ -63,6 +63,10 @@ struct alignas(64) GemmParams {
   long long stats_ld;
   int geglu_f;          // OUT_GEGLU: number of output features F (bias layout [x: F | gate: F])
   int two_cta;          // 1: cta_group::2 kernel (tile pairs; B maps have boxes of BN/2 rows)
+  // nearest-2x-upsample + conv3x3 evaluated as four 2x2 parity convolutions at LOW resolution:
+  // OUT_F32 rows are scattered to pixel (2y + up_py, 2x + up_px) of the [img][2H][2W] output
+  int up_mode, up_py, up_px;
+  double flops_override;  // reference-algorithm FLOPs of this launch for reporting (0 = 2*M*N*K)
 };
 
 // smem bytes for a given BN / stage count (incl. 1 KB alignment slack)

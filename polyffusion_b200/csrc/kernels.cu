@@ -615,6 +615,40 @@ void launch_pack_weight(const float* w, bf16* out_hi, bf16* out_lo, int Cout, in
       w, out_hi, out_lo, Cout, Cin, taps, cout_total, row0, geglu_gran);
 }
 
+// UpSample conv (nearest 2x then 3x3, unet.py:231-238) as four 2x2 parity kernels over the
+// low-resolution input: for output parity (py, px) and tap (a, b) the effective weight is the sum of
+// the 3x3 taps that read the same source pixel.  out: [parity 4][tap 4][Cout][Cin] split bf16.
+__global__ void pack_weight_up_kernel(const float* __restrict__ w, bf16* __restrict__ out_hi,
+                                      bf16* __restrict__ out_lo, int Cout, int Cin) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long per = static_cast<long long>(Cout) * Cin;
+  if (i >= 16 * per) return;
+  const int ci = static_cast<int>(i % Cin);
+  const int co = static_cast<int>((i / Cin) % Cout);
+  const int tap = static_cast<int>((i / per) % 4);
+  const int par = static_cast<int>(i / (4 * per));
+  const int py = par >> 1, px = par & 1, a = tap >> 1, b = tap & 1;
+  // rows of the 3x3 kernel folded into tap a: py=0: {0} | {1,2};  py=1: {0,1} | {2}
+  const int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2);
+  const int ky1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+  const int kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
+  const int kx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+  const float* wp = w + (static_cast<long long>(co) * Cin + ci) * 9;
+  float v = 0.f;
+  for (int ky = ky0; ky <= ky1; ++ky)
+    for (int kx = kx0; kx <= kx1; ++kx) v += wp[ky * 3 + kx];
+  bf16 h, l;
+  split_bf16(v, h, l);
+  out_hi[i] = h;
+  out_lo[i] = l;
+}
+void launch_pack_weight_up(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin,
+                           cudaStream_t s) {
+  const long long total = 16LL * Cout * Cin;
+  pack_weight_up_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, out_hi, out_lo,
+                                                                                   Cout, Cin);
+}
+
 __global__ void vec_add_kernel(const float* a, const float* b, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);

@@ -70,6 +70,9 @@ void launch_conv_out(const float* h, const double* stats, const float* gamma, co
 // geglu_gran > 0: interleave the [x | gate] halves of a GeGLU projection in blocks of geglu_gran rows
 void launch_pack_weight(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin, int taps,
                         int cout_total, int row0, int geglu_gran, cudaStream_t s);
+// UpSample conv weights w [Cout, Cin, 3, 3] -> four 2x2 parity kernels [parity 4][tap 4][Cout][Cin]
+void launch_pack_weight_up(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin,
+                           cudaStream_t s);
 // out[i] = a[i] + b[i] (bias pre-combination); b may be null
 void launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t s);
 

@@ -293,6 +293,26 @@ static PackedW& W(pf_unet* m, const std::string& key, const std::vector<std::str
   return m->packed[key] = pw;
 }
 
+// UpSample conv weight folded into four 2x2 parity kernels (taps = 16: [parity][tap])
+static PackedW& W_up(pf_unet* m, const std::string& name) {
+  const std::string key = name + ":up2x2";
+  auto it = m->packed.find(key);
+  if (it != m->packed.end()) return it->second;
+  PF_CHECK(m->packing, "packed weight '%s' was not prepared by pf_unet_finalize", key.c_str());
+  const RawTensor& r = raw(m, name);
+  PF_CHECK(r.shape.size() == 4 && r.shape[2] == 3 && r.shape[3] == 3, "UpSample weight %s must be 3x3", name.c_str());
+  PackedW pw;
+  pw.rows = static_cast<int>(r.shape[0]);
+  pw.K = static_cast<int>(r.shape[1]);
+  pw.taps = 16;
+  PF_CHECK(pw.K % 64 == 0 && pw.rows % 64 == 0, "UpSample channels must be multiples of 64");
+  const size_t bytes = static_cast<size_t>(16) * pw.rows * pw.K * sizeof(bf16);
+  pw.hi = static_cast<bf16*>(dev_alloc(m, bytes));
+  pw.lo = static_cast<bf16*>(dev_alloc(m, bytes));
+  launch_pack_weight_up(r.ptr, pw.hi, pw.lo, pw.rows, pw.K, m->pack_stream);
+  return m->packed[key] = pw;
+}
+
 static const std::pair<CUtensorMap, CUtensorMap>& wmaps(PackedW& w, int bn, bool dry) {
   auto it = w.maps.find(bn);
   if (it != w.maps.end()) return it->second;
@@ -444,8 +464,18 @@ struct Builder {
     memset(&sg, 0, sizeof sg);
     if (a.kind == 0) fill_taps_1x1(sg);
     else if (a.kind == 1) fill_taps_3x3(sg);
-    else fill_taps_3x3_s2d(sg);
-    PF_CHECK(sg.ntaps == w.taps, "tap count mismatch (%d vs %d)", sg.ntaps, w.taps);
+    else if (a.kind == 2) fill_taps_3x3_s2d(sg);
+    else {  // 3 + parity: 2x2 taps of one output parity of the upsample conv
+      const int par = a.kind - 3, py = par >> 1, px = par & 1;
+      sg.ntaps = 4;
+      sg.img_mul = 1;
+      for (int t = 0; t < 4; ++t) {
+        sg.tap_dy[t] = static_cast<signed char>((t >> 1) - (py == 0 ? 1 : 0));
+        sg.tap_dx[t] = static_cast<signed char>((t & 1) - (px == 0 ? 1 : 0));
+        sg.tap_dq[t] = 0;
+      }
+    }
+    PF_CHECK(a.kind >= 3 ? w.taps == 16 : sg.ntaps == w.taps, "tap count mismatch (%d vs %d)", sg.ntaps, w.taps);
     PF_CHECK(a.C == w.K, "GEMM K mismatch: operand has %d channels, weight expects %d", a.C, w.K);
     sg.kb_per_tap = a.C / 64;
     sg.b_tap_stride = w.rows;
@@ -857,15 +887,24 @@ struct Builder {
   }
 
   T up_sample(const Layer& L, const T& x) {
-    Split a = act_split(x, nullptr, "", 0.f, false, XF_UP2);
+    // conv3x3(nearest2x(x)) == four 2x2 convolutions of x, one per output parity (weights folded at
+    // finalize): 16 tap-GEMMs at low resolution instead of 36, and no 4x upsampled tensor.
+    Split a = act_split(x, nullptr, "", 0.f, false, XF_SAME);
     T y;
     y.C = x.C; y.H = x.H * 2; y.W = x.W * 2;
     y.p = alloc<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
-    ASrc s{a, x.C, y.W, y.H, B, 1};
-    Op& op = conv_gemm(s, W(m, L.name + ".conv.weight", {L.name + ".conv.weight"}), nullptr, nullptr,
-                       y.H, y.W, y.C);
     y.stats = new_stats(y.C);
-    out_f32(op, y.p, y.C, F(m, L.name + ".conv.bias"), 0, nullptr, 0, y.stats);
+    PackedW& w = W_up(m, L.name + ".conv.weight");
+    for (int par = 0; par < 4; ++par) {
+      ASrc s{a, x.C, x.W, x.H, B, 3 + par};
+      Op& op = conv_gemm(s, w, nullptr, nullptr, x.H, x.W, y.C, par * 4 * w.rows);
+      out_f32(op, y.p, y.C, F(m, L.name + ".conv.bias"), 0, nullptr, 0, y.stats);
+      op.g.up_mode = 1;
+      op.g.up_py = par >> 1;
+      op.g.up_px = par & 1;
+      // reference algorithm: 9 taps at 4x the pixels; each parity launch covers a quarter of it
+      op.g.flops_override = 2.0 * (static_cast<double>(B) * x.H * x.W) * y.C * (9.0 * x.C);
+    }
     free_split(a);
     return y;
   }
@@ -1089,6 +1128,7 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
 // algorithmic FLOPs (2*M*N*K, single product: the 3x split is an implementation cost) of a GEMM op
 static double gemm_flops(const Op& op) {
   const GemmParams& g = op.g;
+  if (g.flops_override > 0) return g.flops_override;
   double k = 0;
   for (int s = 0; s < g.nseg; ++s) k += static_cast<double>(g.seg[s].ntaps) * g.seg[s].kb_per_tap * 64;
   return 2.0 * (static_cast<double>(g.m_tiles) * 128 * g.z_count) * (static_cast<double>(g.n_tiles) * op.bn) * k;
@@ -1408,22 +1448,37 @@ int pf_op_conv2d_nhwc(const float* x, int32_t B, int32_t H, int32_t W_, int32_t 
     Builder b(&tm.m, &plan, static_cast<char*>(tm.ws), false, B, 1);
     T xt;
     xt.p = const_cast<float*>(x); xt.C = Cin; xt.H = H; xt.W = W_;
-    const int layout = upsample ? XF_UP2 : (stride == 2 ? XF_S2D : XF_SAME);
-    Split a = b.act_split(xt, nullptr, "", 0.f, false, layout);
-    const int Ho = upsample ? 2 * H : H / stride, Wo = upsample ? 2 * W_ : W_ / stride;
-    Builder::ASrc src{a, Cin, Wo, Ho, stride == 2 ? 4 * B : B, ksize == 1 ? 0 : (stride == 2 ? 2 : 1)};
-    PackedW& pw = W(&tm.m, "w", {"w"});
-    Op& op = b.conv_gemm(src, pw, nullptr, nullptr, Ho, Wo, Cout);
-    if (force_bn) {
-      PF_CHECK(Cout % force_bn == 0, "force_bn does not divide Cout");
-      op.bn = force_bn;
-      op.g.n_tiles = Cout / force_bn;
-      op.g.nstages = op.g.two_cta ? gemm_default_stages2(force_bn) : gemm_default_stages(force_bn);
-      auto& mp = wmaps(pw, op.g.two_cta ? force_bn / 2 : force_bn, false);
-      op.g.seg[0].b_hi = mp.first;
-      op.g.seg[0].b_lo = mp.second;
+    if (upsample) {
+      // same path as UNetModel's UpSample layers: four 2x2 parity convolutions at low resolution
+      PF_CHECK(ksize == 3 && !resid, "upsample op: 3x3 without residual only");
+      Split a = b.act_split(xt, nullptr, "", 0.f, false, XF_SAME);
+      PackedW& pw = W_up(&tm.m, "w");
+      for (int par = 0; par < 4; ++par) {
+        Builder::ASrc src{a, Cin, W_, H, B, 3 + par};
+        Op& op = b.conv_gemm(src, pw, nullptr, nullptr, H, W_, Cout, par * 4 * pw.rows);
+        b.out_f32(op, out, Cout, bias, 0, nullptr, 0);
+        op.g.up_mode = 1;
+        op.g.up_py = par >> 1;
+        op.g.up_px = par & 1;
+      }
+    } else {
+      const int layout = stride == 2 ? XF_S2D : XF_SAME;
+      Split a = b.act_split(xt, nullptr, "", 0.f, false, layout);
+      const int Ho = H / stride, Wo = W_ / stride;
+      Builder::ASrc src{a, Cin, Wo, Ho, stride == 2 ? 4 * B : B, ksize == 1 ? 0 : (stride == 2 ? 2 : 1)};
+      PackedW& pw = W(&tm.m, "w", {"w"});
+      Op& op = b.conv_gemm(src, pw, nullptr, nullptr, Ho, Wo, Cout);
+      if (force_bn) {
+        PF_CHECK(Cout % force_bn == 0, "force_bn does not divide Cout");
+        op.bn = force_bn;
+        op.g.n_tiles = Cout / force_bn;
+        op.g.nstages = op.g.two_cta ? gemm_default_stages2(force_bn) : gemm_default_stages(force_bn);
+        auto& mp = wmaps(pw, op.g.two_cta ? force_bn / 2 : force_bn, false);
+        op.g.seg[0].b_hi = mp.first;
+        op.g.seg[0].b_lo = mp.second;
+      }
+      b.out_f32(op, out, Cout, bias, 0, resid, Cout);
     }
-    b.out_f32(op, out, Cout, bias, 0, resid, Cout);
     run_plan(&tm.m, plan, nullptr, nullptr, nullptr, nullptr, s);
     PF_CUDA(cudaStreamSynchronize(s));
   });
