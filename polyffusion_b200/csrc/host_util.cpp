@@ -161,7 +161,9 @@ int gemm_default_stages2(int bn) {
 }
 
 int choose_bn(int n) {
-  static const int max_bn = env_int("PF_GEMM_MAX_BN", 256);
+  // measured on B200 (profiles/): with cta_group::2, 256x128 tile pairs beat 256x256 on every shape
+  // of this network except the GeGLU projection (which asks for 256 explicitly)
+  static const int max_bn = env_int("PF_GEMM_MAX_BN", 128);
   if (n % 256 == 0 && max_bn >= 256) return 256;
   if (n % 128 == 0 && max_bn >= 128) return 128;
   if (n % 64 == 0) return 64;

@@ -491,8 +491,8 @@ struct Builder {
   // conv / linear GEMM over B images of Ho x Wo output pixels.
   // seg1 (optional) is a 1x1 segment accumulated into the same tile (ResBlock skip conv).
   Op& conv_gemm(const ASrc& a0, PackedW& w0, const ASrc* a1, PackedW* w1, int Ho, int Wo, int Cout,
-                int row0 = 0) {
-    const int bn = choose_bn(Cout);
+                int row0 = 0, int bn_override = 0) {
+    const int bn = bn_override ? bn_override : choose_bn(Cout);
     const int box_w = choose_box_w(Wo);
     PF_CHECK(128 % box_w == 0 && Wo % box_w == 0, "unsupported width %d", Wo);
     const int box_h = 128 / box_w;
@@ -829,11 +829,11 @@ struct Builder {
       {
         // GeGLU fused into the projection's epilogue: weight rows are interleaved so every BN-wide
         // tile holds [BN/2 value | BN/2 gate] columns of the same output features
-        const int bn = choose_bn(2 * Fh);
+        const int bn = (2 * Fh) % 256 == 0 ? 256 : choose_bn(2 * Fh);
         ASrc s{l3, C, Wd, H, B, 0};
         Op& op = conv_gemm(s, W(m, tb + ".ff.net.0.proj.weight:geglu" + std::to_string(bn / 2),
                                 {tb + ".ff.net.0.proj.weight"}, bn / 2),
-                           nullptr, nullptr, H, Wd, 2 * Fh);
+                           nullptr, nullptr, H, Wd, 2 * Fh, 0, bn);
         op.g.mode = OUT_GEGLU;
         op.g.out_hi = e.hi; op.g.out_lo = e.lo; op.g.ldc = Fh;
         op.g.addvec = F(m, tb + ".ff.net.0.proj.bias");
