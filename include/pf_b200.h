@@ -123,6 +123,15 @@ int pf_sample_step_ddpm_legacy(const pf_step_args* a, pf_stream stream);
 int pf_q_sample(const float* x0, const float* noise, float* out, int64_t n, float a, float b,
                 pf_stream stream);
 
+/* get_mask(orig, "below" | "above") -- inference_sdf.py:132-180, batched over songs.
+ * orig / mask [n_seg, channels, steps, pitches] fp32 (channel 0 = onsets); every seg_per_song
+ * consecutive segments form one song whose rows are scanned as one sequence (the reference scans the
+ * whole batch as one sequence: seg_per_song = n_seg).  above = 0: keep pitch >= lowest onset
+ * (inpaint accompaniment below a melody); above = 1: keep pitch <= highest onset.  Synchronises;
+ * fails if a song has no onset (the reference raises IndexError). */
+int pf_get_mask(const float* orig, float* mask, int32_t n_seg, int32_t seg_per_song, int32_t channels,
+                int32_t steps, int32_t pitches, int32_t above, pf_stream stream);
+
 /* Building-block ops (used by the parity tests; they allocate their own scratch and synchronise).
  * conv: x NHWC fp32 [B,H,W,Cin] (Cin%64==0), w [Cout,Cin,k,k] (k in {1,3}), stride in {1,2},
  * upsample in {0,1} (nearest 2x before the conv), bias/resid optional; out NHWC [B,Ho,Wo,Cout]. */

@@ -153,5 +153,58 @@ def main():
     save("legacy_ddpm.npz", x_T=xT, tape_seed=51, out=xx, beta=dd.beta, alpha_bar=dd.alpha_bar)
 
 
+def reference_glue_functions():
+    """get_mask / get_autoreg_data lifted from inference_sdf.py:121-193 by ast (the module itself
+    needs pretty_midi / omegaconf / matplotlib)."""
+    import ast
+
+    src = open(os.path.join(reference_loader.REFERENCE_ROOT, "inference_sdf.py")).read()
+    ns = {"torch": torch}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("get_mask", "get_autoreg_data"):
+            exec(compile(ast.Module([node], []), "inference_sdf.py", "exec"), ns)
+    return ns["get_mask"], ns["get_autoreg_data"]
+
+
+def synthetic_melody(n_seg, seed, blank_first=0, pitch0=False):
+    """Synthetic melody prmat2c (BASELINE config 5): per time step an onset at pitch U{60..84} with
+    probability 0.25 (sometimes a second, lower one) in channel 0; binary fp32."""
+    g = torch.Generator().manual_seed(seed)
+    o = torch.zeros(n_seg, 2, 128, 128)
+    for b in range(n_seg):
+        for t in range(128):
+            if b == 0 and t < blank_first:
+                continue
+            if torch.rand(1, generator=g) < 0.25:
+                o[b, 0, t, int(torch.randint(60, 85, (1,), generator=g))] = 1
+                if torch.rand(1, generator=g) < 0.3:
+                    o[b, 0, t, int(torch.randint(30, 60, (1,), generator=g))] = 1
+    if pitch0:
+        o[0, 0, 5, 0] = 1
+    return o
+
+
+def make_mask_golden():
+    get_mask, get_autoreg = reference_glue_functions()
+    out = {}
+    for i, (n_seg, seed, blank, p0) in enumerate([(2, 1, 0, False), (3, 2, 7, False), (1, 3, 0, True), (4, 4, 20, True)]):
+        o = synthetic_melody(n_seg, seed, blank, p0)
+        out[f"case{i}_args"] = np.asarray([n_seg, seed, blank, int(p0)])
+        # masks are binary: store packed bits
+        out[f"case{i}_below"] = np.packbits(get_mask(o, "below").contiguous().numpy().astype(np.uint8))
+        out[f"case{i}_above"] = np.packbits(get_mask(o, "above").contiguous().numpy().astype(np.uint8))
+    g = torch.Generator().manual_seed(9)
+    d = torch.randn(4, 2, 8, 4, generator=g)
+    out["autoreg_in"] = d.numpy()
+    out["autoreg_out"] = get_autoreg(d, 2).numpy()
+    save("mask_autoreg.npz", **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "masks":
+        os.makedirs(OUT, exist_ok=True)
+        reference_loader.load()
+        make_mask_golden()
+    else:
+        main()
+        make_mask_golden()

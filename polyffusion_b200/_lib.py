@@ -84,6 +84,10 @@ SYMBOLS = {
     "pf_sample_step_ddim": (c_int32, [POINTER(StepArgs), c_void_p]),
     "pf_sample_step_ddpm_legacy": (c_int32, [POINTER(StepArgs), c_void_p]),
     "pf_q_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),
+    "pf_get_mask": (
+        c_int32,
+        [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    ),
     "pf_op_conv2d_nhwc": (
         c_int32,
         [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,

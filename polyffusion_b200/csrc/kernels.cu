@@ -649,6 +649,84 @@ void launch_pack_weight_up(const float* w, bf16* out_hi, bf16* out_lo, int Cout,
                                                                                    Cout, Cin);
 }
 
+// ------------------------------------------------------------------------------------------------
+// get_mask("below" / "above") of inference_sdf.py:132-180 on the GPU, batched over songs.
+// orig [n_seg, C, T, P] (channel 0 = onsets); each song = seg_per_song consecutive segments whose
+// T-step rows form one sequence.  Per row: below -> first-maximum index of the onset row (0 when the
+// row is empty), above -> P-1 - first-maximum index of the flipped row (P-1 when empty); rows whose
+// value equals the "empty" value inherit the previous row's value (leading ones take the first
+// non-empty value); mask[row, pitch >= v] = 1 (below) or mask[row, pitch <= v] = 1 (above).
+// ------------------------------------------------------------------------------------------------
+__global__ void mask_row_extreme_kernel(const float* __restrict__ orig, int* __restrict__ rowval,
+                                        int C, int T, int P, int above, long long rows) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long seg = row / T, t = row % T;
+  const float* rp = orig + ((seg * C + 0) * T + t) * P;
+  // first index of the maximum, scanning pitches upward (below) or downward (above)
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int k = lane; k < P; k += 32) {
+    const int pidx = above ? (P - 1 - k) : k;
+    const float v = rp[pidx];
+    if (v > best || (v == best && k < bi)) { best = v; bi = k; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) rowval[row] = above ? (P - 1 - bi) : bi;
+}
+
+__global__ void mask_fill_kernel(int* __restrict__ rowval, int rows_per_song, int n_songs, int empty,
+                                 int* __restrict__ err) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_songs) return;
+  int* v = rowval + static_cast<long long>(s) * rows_per_song;
+  // first row whose value is non-zero (min_pitch.nonzero()[0] / max_pitch.nonzero()[0]); the
+  // reference raises IndexError when there is none
+  int first = -1;
+  for (int i = 0; i < rows_per_song; ++i)
+    if (v[i] != 0) { first = i; break; }
+  if (first < 0) { atomicExch(err, 1); return; }
+  const int fv = v[first];
+  for (int i = 0; i < first; ++i) v[i] = fv;
+  // rows with the "empty" value (0 below, P-1 above) inherit the previous row; index -1 wraps to the
+  // last row exactly like the reference's Python indexing
+  for (int i = 0; i < rows_per_song; ++i)
+    if (v[i] == empty) v[i] = v[i > 0 ? i - 1 : rows_per_song - 1];
+}
+
+__global__ void mask_write_kernel(const int* __restrict__ rowval, float* __restrict__ mask, int C, int T,
+                                  int P, int above, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int pch = static_cast<int>(i % P);
+  const long long r = i / P;
+  const int t = static_cast<int>(r % T);
+  const long long sc = r / T;  // seg * C + c
+  const long long seg = sc / C;
+  const int v = rowval[seg * T + t];
+  mask[i] = above ? (pch <= v ? 1.f : 0.f) : (pch >= v ? 1.f : 0.f);
+}
+
+int launch_get_mask(const float* orig, float* mask, int* rowval, int* err, int n_seg, int seg_per_song,
+                    int C, int T, int P, int above, cudaStream_t s) {
+  const long long rows = static_cast<long long>(n_seg) * T;
+  const int n_songs = n_seg / seg_per_song;
+  mask_row_extreme_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(orig, rowval, C, T, P,
+                                                                                above, rows);
+  mask_fill_kernel<<<(n_songs + 63) / 64, 64, 0, s>>>(rowval, seg_per_song * T, n_songs,
+                                                      above ? P - 1 : 0, err);
+  const long long total = static_cast<long long>(n_seg) * C * T * P;
+  mask_write_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(rowval, mask, C, T, P,
+                                                                               above, total);
+  return 0;
+}
+
 __global__ void vec_add_kernel(const float* a, const float* b, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);

@@ -73,6 +73,10 @@ void launch_pack_weight(const float* w, bf16* out_hi, bf16* out_lo, int Cout, in
 // UpSample conv weights w [Cout, Cin, 3, 3] -> four 2x2 parity kernels [parity 4][tap 4][Cout][Cin]
 void launch_pack_weight_up(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin,
                            cudaStream_t s);
+// get_mask("below"/"above") of inference_sdf.py:132-180, batched over songs (see kernels.cu).
+// rowval: scratch [n_seg * T] ints; err: device int set to 1 if a song has no onset at all.
+int launch_get_mask(const float* orig, float* mask, int* rowval, int* err, int n_seg, int seg_per_song,
+                    int C, int T, int P, int above, cudaStream_t s);
 // out[i] = a[i] + b[i] (bias pre-combination); b may be null
 void launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t s);
 

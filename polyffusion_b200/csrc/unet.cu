@@ -1383,6 +1383,25 @@ int pf_sample_step_ddpm_legacy(const pf_step_args* a, pf_stream stream) {
     PF_CUDA(cudaGetLastError());
   });
 }
+int pf_get_mask(const float* orig, float* mask, int32_t n_seg, int32_t seg_per_song, int32_t channels,
+                int32_t steps, int32_t pitches, int32_t above, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(orig && mask && n_seg > 0 && seg_per_song > 0 && n_seg % seg_per_song == 0,
+             "bad get_mask arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int* scratch = nullptr;
+    PF_CUDA(cudaMalloc(&scratch, (static_cast<size_t>(n_seg) * steps + 1) * sizeof(int)));
+    int* err = scratch + static_cast<size_t>(n_seg) * steps;
+    PF_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
+    launch_get_mask(orig, mask, scratch, err, n_seg, seg_per_song, channels, steps, pitches, above, s);
+    int herr = 0;
+    PF_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PF_CUDA(cudaStreamSynchronize(s));
+    cudaFree(scratch);
+    PF_CHECK(herr == 0, "get_mask: a song has no onset at all (the reference raises IndexError here)");
+  });
+}
+
 int pf_q_sample(const float* x0, const float* noise, float* out, int64_t n, float a, float b,
                 pf_stream stream) {
   return guarded([&] {
