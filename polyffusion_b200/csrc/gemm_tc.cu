@@ -43,7 +43,10 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, long long 
 // 128 A rows and HALF of the B rows (the MMA reads the other half from the peer's smem), so a stage
 // is 32 KB + BN*128 B instead of 32 KB + BN*256 B: more k-blocks in flight per SM and 1/3 fewer
 // operand bytes through L2.  Only the leader CTA issues MMAs; both run the epilogue on their rows.
-template <int BN, bool TWO>
+// MODE / STATS are compile-time so that every kernel carries only ONE epilogue variant: the fully
+// general kernel was ~100 KB of SASS and the short (K = 256) launches stalled on instruction fetch
+// (ncu: 35 % of samples `stall_no_inst`).
+template <int BN, bool TWO, int MODE, bool STATS>
 __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -213,13 +216,27 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
       const long long m0 = static_cast<long long>(tc.tile) * GEMM_BM + q * 32;  // first row of this warp
       const long long zoff = tc.zb * p.out_zb + tc.zh * p.out_zh;
-      if (p.mode == OUT_F32 && p.resid != nullptr) {
-        // pull this warp's share of the residual tile into L2 while the main loop is still running
-        // (one 128-byte line per (row, 32-column chunk)); the register prefetch below then hits L2
+      if (MODE == OUT_F32 && p.resid != nullptr) {
+        // Pull this warp's share of the residual into L2 one tile AHEAD (the residual was written
+        // several kernels ago and has usually left L2; a DRAM round trip per chunk would otherwise
+        // dominate the epilogue of the small-K GEMMs): one 128-byte line per (row, 32-col chunk).
+        // The first tile of the CTA is prefetched here too, while its main loop is still running.
+        const long long tn = t + wstride;
+        if (tn < total_tiles) {
+          const TileCoord nc = decode_tile(p, tn, BN, TWO ? static_cast<int>(rank) : -1);
 #pragma unroll
-        for (int ci = 0; ci < BN / 64; ++ci) {
-          const float* ptr = p.resid + (m0 + lane) * p.ldr + tc.n0 + chalf * 32 + ci * 64;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+          for (int ci = 0; ci < BN / 64; ++ci) {
+            const float* ptr = p.resid + (static_cast<long long>(nc.tile) * GEMM_BM + q * 32 + lane) * p.ldr +
+                               nc.n0 + chalf * 32 + ci * 64;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+          }
+        }
+        if (lt == 0) {
+#pragma unroll
+          for (int ci = 0; ci < BN / 64; ++ci) {
+            const float* ptr = p.resid + (m0 + lane) * p.ldr + tc.n0 + chalf * 32 + ci * 64;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+          }
         }
       }
       mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
@@ -227,7 +244,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
 
-      if (p.mode == OUT_SPLIT_T) {
+      if constexpr (MODE == OUT_SPLIT_T) {
         // [img][n][token]; consecutive lanes -> consecutive tokens (already coalesced)
         const long long tok = static_cast<long long>(tc.trem) * GEMM_BM + q * 32 + lane;
         const long long base = zoff + static_cast<long long>(tc.img) * p.out_img + tok;
@@ -246,13 +263,13 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           }
         }
       } else {
-        const bool geglu = (p.mode == OUT_GEGLU);
+        constexpr bool geglu = (MODE == OUT_GEGLU);
         const int ncols = geglu ? BN / 2 : BN;          // output columns produced by this tile
         const int ocol0 = geglu ? (tc.n0 / 2) : tc.n0;  // first output column
         const float* av = p.addvec ? p.addvec + static_cast<long long>(tc.img) * p.addvec_ld : nullptr;
-        const bool has_res = (p.mode == OUT_F32) && p.resid != nullptr;
-        float4 csum[BN / 64], csq[BN / 64];  // per-chunk column partial sums (lanes < 8 after shuffles)
-#pragma unroll
+        const bool has_res = (MODE == OUT_F32) && p.resid != nullptr;
+        float4 csum[STATS ? BN / 64 : 1], csq[STATS ? BN / 64 : 1];  // per-chunk column partial sums
+#pragma unroll(STATS ? BN / 64 : 1)
         for (int ci = 0; ci < BN / 64; ++ci) {
           const int c = chalf * 32 + ci * 64;
           if (c >= ncols) break;
@@ -266,7 +283,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           {
             uint32_t v[32];
             tmem_ld32(taddr + c, v);
-            if (geglu) {
+            if constexpr (geglu) {
               uint32_t g[32];
               tmem_ld32(taddr + BN / 2 + c, g);
               tmem_ld_wait();
@@ -318,14 +335,16 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
               const int Wl = p.tiles_x * p.box_w, Hl = (p.tiles_per_img / p.tiles_x) * p.box_h;
               m = (static_cast<long long>(tc.img) * (2 * Hl) + 2 * y + p.up_py) * (2 * Wl) + 2 * x + p.up_px;
             }
-            if (p.mode == OUT_F32) {
+            if constexpr (MODE == OUT_F32) {
               if (has_res) {
                 o.x += rres[it].x; o.y += rres[it].y; o.z += rres[it].z; o.w += rres[it].w;
               }
               *reinterpret_cast<float4*>(p.out + zoff + m * p.ldc + tc.n0 + c + c4) = o;
-              ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
-              ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y);
-              ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+              if constexpr (STATS) {
+                ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
+                ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y);
+                ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+              }
             } else {  // OUT_SPLIT / OUT_GEGLU: split-bf16 row-major
               uint2 h, l;
               split2(o.x, o.y, h.x, l.x);
@@ -335,7 +354,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
               *reinterpret_cast<uint2*>(p.out_lo + off) = l;
             }
           }
-          if (p.stats) {
+          if constexpr (STATS) {
             // reduce over the 4 row-groups of the warp (lanes with equal lane&7)
 #pragma unroll
             for (int o = 8; o <= 16; o <<= 1) {
@@ -353,7 +372,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           }
           __syncwarp();
         }
-        if (p.stats && lane < 8) {
+        if (STATS && lane < 8) {
           // park the partials in this warp's (now idle) staging tile: [chunk][sum | sq][32 cols]
 #pragma unroll
           for (int ci = 0; ci < BN / 64; ++ci) {
@@ -369,7 +388,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         if (TWO) mbar_arrive_leader(smem_u32(&tmem_empty_bar[as]));
         else mbar_arrive(smem_u32(&tmem_empty_bar[as]));
       }
-      if (p.stats) {
+      if constexpr (STATS) {
         // flush this tile's column sums: [img][stats_ld][2] fp64
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et < BN) {
@@ -400,56 +419,82 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   }
 }
 
-template <int BN>
+template <int BN, int MODE, bool STATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  gemm_body<BN, false>(p);
+  gemm_body<BN, false, MODE, STATS>(p);
 }
 
-template <int BN>
+template <int BN, int MODE, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
-  gemm_body<BN, true>(p);
+  gemm_body<BN, true, MODE, STATS>(p);
+}
+
+typedef void (*GemmKernel)(GemmParams);
+
+// variant index: 0 = fp32, 1 = fp32 + GroupNorm statistics, 2 = split, 3 = split transposed, 4 = GeGLU
+template <int BN, bool TWO>
+static GemmKernel pick_variant(int v) {
+  if (TWO) {
+    switch (v) {
+      case 0: return gemm_tc2_kernel<BN, OUT_F32, false>;
+      case 1: return gemm_tc2_kernel<BN, OUT_F32, true>;
+      case 2: return gemm_tc2_kernel<BN, OUT_SPLIT, false>;
+      case 3: return gemm_tc2_kernel<BN, OUT_SPLIT_T, false>;
+      default: return gemm_tc2_kernel<BN, OUT_GEGLU, false>;
+    }
+  }
+  switch (v) {
+    case 0: return gemm_tc_kernel<BN, OUT_F32, false>;
+    case 1: return gemm_tc_kernel<BN, OUT_F32, true>;
+    case 2: return gemm_tc_kernel<BN, OUT_SPLIT, false>;
+    case 3: return gemm_tc_kernel<BN, OUT_SPLIT_T, false>;
+    default: return gemm_tc_kernel<BN, OUT_GEGLU, false>;
+  }
+}
+
+static GemmKernel pick_kernel(int bn, bool two, int v) {
+  switch (bn) {
+    case 64: return two ? pick_variant<64, true>(v) : pick_variant<64, false>(v);
+    case 128: return two ? pick_variant<128, true>(v) : pick_variant<128, false>(v);
+    case 256: return two ? pick_variant<256, true>(v) : pick_variant<256, false>(v);
+    default: return nullptr;
+  }
 }
 
 cudaError_t gemm_init_attrs() {
-  cudaError_t e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  return e;
+  for (int bn : {64, 128, 256})
+    for (int two = 0; two < 2; ++two)
+      for (int v = 0; v < 5; ++v) {
+        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_kernel(bn, two != 0, v)),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) return e;
+      }
+  return cudaSuccess;
 }
 
 cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t stream) {
+  int v;
+  switch (p.mode) {
+    case OUT_F32: v = p.stats ? 1 : 0; break;
+    case OUT_SPLIT: v = 2; break;
+    case OUT_SPLIT_T: v = 3; break;
+    default: v = 4; break;
+  }
+  GemmKernel k = pick_kernel(bn, p.two_cta != 0, v);
+  if (!k) return cudaErrorInvalidValue;
   if (p.two_cta) {
     const int smem = p.nstages * gemm_stage_bytes2(bn) + 1024 + gemm_epilogue_smem_bytes(bn);
     const long long pairs = static_cast<long long>(p.n_tiles) * (p.m_tiles / 2) * p.z_count;
     const long long max_clusters = num_ctas / 2;
     const unsigned grid = 2u * static_cast<unsigned>(pairs < max_clusters ? pairs : max_clusters);
-    switch (bn) {
-      case 64: gemm_tc2_kernel<64><<<grid, GEMM_THREADS, smem, stream>>>(p); break;
-      case 128: gemm_tc2_kernel<128><<<grid, GEMM_THREADS, smem, stream>>>(p); break;
-      case 256: gemm_tc2_kernel<256><<<grid, GEMM_THREADS, smem, stream>>>(p); break;
-      default: return cudaErrorInvalidValue;
-    }
+    k<<<grid, GEMM_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
   }
   const int smem = gemm_smem_bytes(bn, p.nstages) + gemm_epilogue_smem_bytes(bn);
   const long long total = static_cast<long long>(p.n_tiles) * p.m_tiles * p.z_count;
   const unsigned grid = static_cast<unsigned>(total < num_ctas ? total : num_ctas);
-  switch (bn) {
-    case 64: gemm_tc_kernel<64><<<grid, GEMM_THREADS, smem, stream>>>(p); break;
-    case 128: gemm_tc_kernel<128><<<grid, GEMM_THREADS, smem, stream>>>(p); break;
-    case 256: gemm_tc_kernel<256><<<grid, GEMM_THREADS, smem, stream>>>(p); break;
-    default: return cudaErrorInvalidValue;
-  }
+  k<<<grid, GEMM_THREADS, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

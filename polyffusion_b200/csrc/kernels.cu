@@ -17,6 +17,7 @@ __device__ __forceinline__ float silu_fast(float v) {
 // conv_in: NCHW fp32 (tiny Cin) -> NHWC fp32, 3x3 pad 1.
 // block = 256 threads = 64 pixels of one row x 4 channel quarters.
 // ------------------------------------------------------------------------------------------------
+constexpr int CI_ROWS = 4;  // image rows per block (amortises the weight / halo fill)
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x,
                                                       const float* __restrict__ w,
                                                       const float* __restrict__ bias,
@@ -25,53 +26,60 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   extern __shared__ float sm[];
   const int K = Cin * 9;
   float* sw = sm;                    // [K][Cout]
-  float* sx = sm + K * Cout;         // [Cin][3][66]
-  const int b = blockIdx.z, y = blockIdx.y, xb = blockIdx.x * 64;
+  float* sx = sm + K * Cout;         // [Cin][CI_ROWS + 2][66]
+  const int b = blockIdx.z, y0 = blockIdx.y * CI_ROWS, xb = blockIdx.x * 64;
+  // destination-ordered fill (consecutive threads -> consecutive smem words: no bank conflicts);
+  // the strided global reads of the 4.6 KB weight tensor are L2 hits
   for (int i = threadIdx.x; i < K * Cout; i += 256) {
-    const int co = i / K, k = i % K;  // w is [Cout][Cin][3][3] -> k = ci*9 + ky*3 + kx
-    sw[k * Cout + co] = w[i];
+    const int k = i / Cout, co = i % Cout;  // w is [Cout][Cin][3][3] -> k = ci*9 + ky*3 + kx
+    sw[i] = __ldg(w + co * K + k);
   }
-  for (int i = threadIdx.x; i < Cin * 3 * 66; i += 256) {
-    const int ci = i / (3 * 66), r = (i / 66) % 3, xx = i % 66;
-    const int gy = y + r - 1, gx = xb + xx - 1;
+  const int HR = CI_ROWS + 2;
+  for (int i = threadIdx.x; i < Cin * HR * 66; i += 256) {
+    const int ci = i / (HR * 66), r = (i / 66) % HR, xx = i % 66;
+    const int gy = y0 + r - 1, gx = xb + xx - 1;
     float v = 0.f;
     if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-      v = x[((static_cast<long long>(b) * Cin + ci) * H + gy) * W + gx];
+      v = __ldg(x + ((static_cast<long long>(b) * Cin + ci) * H + gy) * W + gx);
     sx[i] = v;
   }
   __syncthreads();
   const int p = threadIdx.x >> 2, q = threadIdx.x & 3;
-  const int cpq = Cout / 4;  // channels per quarter (16 for Cout = 64)
   if (xb + p >= W) return;
-  float* o = out + ((static_cast<long long>(b) * H + y) * W + xb + p) * Cout + q * cpq;
-  // cpq == 16 (checked by the host): 16 accumulators per thread, weights broadcast from smem
-  float4 acc[4];
+  // Cout / 4 == 16 (checked by the host): 16 accumulators per thread, weights broadcast from smem
+  float4 bv[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] = *reinterpret_cast<const float4*>(bias + q * 16 + 4 * j);
-  for (int ci = 0; ci < Cin; ++ci)
+  for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(bias + q * 16 + 4 * j);
+  for (int rr = 0; rr < CI_ROWS; ++rr) {
+    const int y = y0 + rr;
+    if (y >= H) break;
+    float4 acc[4] = {bv[0], bv[1], bv[2], bv[3]};
+    for (int ci = 0; ci < Cin; ++ci)
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float v = sx[(ci * 3 + r) * 66 + p + kx];
-        const float* wr = sw + (ci * 9 + r * 3 + kx) * Cout + q * 16;
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = sx[(ci * HR + rr + r) * 66 + p + kx];
+          const float* wr = sw + (ci * 9 + r * 3 + kx) * Cout + q * 16;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 ww = *reinterpret_cast<const float4*>(wr + 4 * j);
-          acc[j].x = fmaf(v, ww.x, acc[j].x);
-          acc[j].y = fmaf(v, ww.y, acc[j].y);
-          acc[j].z = fmaf(v, ww.z, acc[j].z);
-          acc[j].w = fmaf(v, ww.w, acc[j].w);
+          for (int j = 0; j < 4; ++j) {
+            const float4 ww = *reinterpret_cast<const float4*>(wr + 4 * j);
+            acc[j].x = fmaf(v, ww.x, acc[j].x);
+            acc[j].y = fmaf(v, ww.y, acc[j].y);
+            acc[j].z = fmaf(v, ww.z, acc[j].z);
+            acc[j].w = fmaf(v, ww.w, acc[j].w);
+          }
         }
-      }
+    float* o = out + ((static_cast<long long>(b) * H + y) * W + xb + p) * Cout + q * 16;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(o + 4 * j) = acc[j];
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(o + 4 * j) = acc[j];
+  }
 }
 
 void launch_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int Cin,
                     int H, int W, int Cout, cudaStream_t s) {
-  dim3 grid((W + 63) / 64, H, B);
-  const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + Cin * 3 * 66) * sizeof(float);
+  dim3 grid((W + 63) / 64, (H + CI_ROWS - 1) / CI_ROWS, B);
+  const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + Cin * (CI_ROWS + 2) * 66) * sizeof(float);
   conv_in_kernel<<<grid, 256, smem, s>>>(x, w, bias, out, Cin, H, W, Cout);
 }
 
@@ -529,19 +537,39 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__
     const int tap = r / C, c = r % C;
     sw[i] = w[(static_cast<long long>(co) * C + c) * 9 + tap];
   }
-  for (int i = threadIdx.x; i < (CO_T + 2) * (CO_T + 2) * c4n; i += 256) {
-    const int pix = i / c4n, c = (i % c4n) * 4;
-    const int gy = ty + pix / (CO_T + 2) - 1, gx = tx + pix % (CO_T + 2) - 1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(
-          h + ((static_cast<long long>(b) * H + gy) * W + gx) * C + c));
-      v.x = silu_fast(fmaf(a.x, sc[c + 0], sh[c + 0]));
-      v.y = silu_fast(fmaf(a.y, sc[c + 1], sh[c + 1]));
-      v.z = silu_fast(fmaf(a.z, sc[c + 2], sh[c + 2]));
-      v.w = silu_fast(fmaf(a.w, sc[c + 3], sh[c + 3]));
+  const int nfill = (CO_T + 2) * (CO_T + 2) * c4n;
+  for (int i0 = threadIdx.x; i0 < nfill; i0 += 256 * 4) {
+    float4 a[4];
+    int ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // issue the four global loads first (latency overlap)
+      const int i = i0 + u * 256;
+      ok[u] = 0;
+      a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < nfill) {
+        const int pix = i / c4n, c = (i % c4n) * 4;
+        const int gy = ty + pix / (CO_T + 2) - 1, gx = tx + pix % (CO_T + 2) - 1;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          ok[u] = 1;
+          a[u] = __ldg(reinterpret_cast<const float4*>(
+              h + ((static_cast<long long>(b) * H + gy) * W + gx) * C + c));
+        }
+      }
     }
-    *reinterpret_cast<float4*>(st + pix * pitch + c) = v;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      if (i >= nfill) break;
+      const int pix = i / c4n, c = (i % c4n) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok[u]) {
+        v.x = silu_fast(fmaf(a[u].x, sc[c + 0], sh[c + 0]));
+        v.y = silu_fast(fmaf(a[u].y, sc[c + 1], sh[c + 1]));
+        v.z = silu_fast(fmaf(a[u].z, sc[c + 2], sh[c + 2]));
+        v.w = silu_fast(fmaf(a[u].w, sc[c + 3], sh[c + 3]));
+      }
+      *reinterpret_cast<float4*>(st + pix * pitch + c) = v;
+    }
   }
   __syncthreads();
   const int py = threadIdx.x / CO_T, px = threadIdx.x % CO_T;
