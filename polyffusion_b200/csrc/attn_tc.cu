@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -289,8 +291,7 @@ cudaError_t attn_init_attrs() {
 cudaError_t launch_attn(const AttnParams& p, int num_ctas, cudaStream_t stream) {
   const long long items = static_cast<long long>(p.B) * p.heads * (p.N / 128);
   const unsigned grid = static_cast<unsigned>(items < num_ctas ? items : num_ctas);
-  attn_tc_kernel<<<grid, ATTN_THREADS, attn_smem_bytes(), stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(attn_tc_kernel, dim3(grid), dim3(ATTN_THREADS), attn_smem_bytes(), stream, p);
 }
 
 }  // namespace pf

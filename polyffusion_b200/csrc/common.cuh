@@ -6,7 +6,28 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <utility>
+
 namespace pf {
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  // measured on B200: no gain on this step (22.24 ms with vs 22.00 ms without), so opt-in only
+  static const bool enabled = std::getenv("PF_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -20,6 +41,18 @@ __device__ __forceinline__ bool elect_one() {
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(pred));
   return pred != 0;
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// With PF_PDL=1 every hot-path kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: its
+// CTAs may be scheduled while the tail of the previous kernel is still running, do their private
+// prologue (barrier init, TMEM alloc, descriptor prefetch), and block in pdl_wait() until the previous
+// kernel has completed and flushed.  Rule: nothing produced by an earlier kernel is read, and no
+// global memory is written, before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- mbarrier

@@ -108,6 +108,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   if (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();     // operands / residual / statistics of earlier kernels are complete from here on
+  pdl_trigger();  // let the next kernel's CTAs start their prologue during our tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -488,14 +490,12 @@ cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t 
     const long long pairs = static_cast<long long>(p.n_tiles) * (p.m_tiles / 2) * p.z_count;
     const long long max_clusters = num_ctas / 2;
     const unsigned grid = 2u * static_cast<unsigned>(pairs < max_clusters ? pairs : max_clusters);
-    k<<<grid, GEMM_THREADS, smem, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(k, dim3(grid), dim3(GEMM_THREADS), smem, stream, p);
   }
   const int smem = gemm_smem_bytes(bn, p.nstages) + gemm_epilogue_smem_bytes(bn);
   const long long total = static_cast<long long>(p.n_tiles) * p.m_tiles * p.z_count;
   const unsigned grid = static_cast<unsigned>(total < num_ctas ? total : num_ctas);
-  k<<<grid, GEMM_THREADS, smem, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(k, dim3(grid), dim3(GEMM_THREADS), smem, stream, p);
 }
 
 }  // namespace pf

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
                                                       const float* __restrict__ bias,
                                                       float* __restrict__ out, int Cin, int H, int W,
                                                       int Cout) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int K = Cin * 9;
   float* sw = sm;                    // [K][Cout]
@@ -80,7 +82,7 @@ void launch_conv_in(const float* x, const float* w, const float* bias, float* ou
                     int H, int W, int Cout, cudaStream_t s) {
   dim3 grid((W + 63) / 64, (H + CI_ROWS - 1) / CI_ROWS, B);
   const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + Cin * (CI_ROWS + 2) * 66) * sizeof(float);
-  conv_in_kernel<<<grid, 256, smem, s>>>(x, w, bias, out, Cin, H, W, Cout);
+  launch_pdl(conv_in_kernel, grid, dim3(256), smem, s, x, w, bias, out, Cin, H, W, Cout);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -89,6 +91,8 @@ void launch_conv_in(const float* x, const float* w, const float* bias, float* ou
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ src,
                                                        double* __restrict__ acc, int HW, int Cs,
                                                        int Ctot, int coff, int pix_per_block) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_sum[256 * 4];
   __shared__ float s_sq[256 * 4];
   const int b = blockIdx.y;
@@ -130,7 +134,7 @@ void launch_gn_stats(const float* src, double* acc, int B, int HW, int Cs, int C
   int ppb = (HW + chunks - 1) / chunks;
   chunks = (HW + ppb - 1) / ppb;
   dim3 grid(chunks, B);
-  gn_stats_kernel<<<grid, 256, 0, s>>>(src, acc, HW, Cs, Ctot, coff, ppb);
+  launch_pdl(gn_stats_kernel, grid, dim3(256), 0, s, src, acc, HW, Cs, Ctot, coff, ppb);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -155,6 +159,8 @@ __device__ __forceinline__ void store_split16(const float* v, bf16* oh, bf16* ol
 }
 
 __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_scale[512], s_shift[512];
   const int C = a.C0 + a.C1;
   const int b = blockIdx.y;
@@ -238,7 +244,7 @@ void launch_act_split(const ActSplitArgs& a, cudaStream_t s) {
   const int C = a.C0 + a.C1;
   const long long items = static_cast<long long>(a.H) * a.W * (C >> 4);
   dim3 grid(static_cast<unsigned>((items + 256 * AS_IPT - 1) / (256 * AS_IPT)), a.B);
-  act_split_kernel<<<grid, 256, 0, s>>>(a);
+  launch_pdl(act_split_kernel, grid, dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,6 +267,8 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
                                                        bf16* __restrict__ out_hi,
                                                        bf16* __restrict__ out_lo, long long rows,
                                                        int C) {
+  pdl_wait();
+  pdl_trigger();
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
 void launch_ln_split(const float* src, const float* gamma, const float* beta, float eps,
                      bf16* out_hi, bf16* out_lo, long long rows, int C, cudaStream_t s) {
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
-  ln_split_kernel<<<blocks, 256, 0, s>>>(src, gamma, beta, eps, out_hi, out_lo, rows, C);
+  launch_pdl(ln_split_kernel, dim3(blocks), dim3(256), 0, s, src, gamma, beta, eps, out_hi, out_lo, rows, C);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -405,6 +413,8 @@ void launch_softmax_split(const float* S, float scale, bf16* out_hi, bf16* out_l
 __global__ void time_sinusoid_kernel(const long long* __restrict__ t,
                                      const float* __restrict__ freqs, float* __restrict__ out, int B,
                                      int half) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
   const int b = i / half, j = i % half;
@@ -416,7 +426,7 @@ __global__ void time_sinusoid_kernel(const long long* __restrict__ t,
 }
 void launch_time_sinusoid(const long long* t, const float* freqs, float* out, int B, int half,
                           cudaStream_t s) {
-  time_sinusoid_kernel<<<(B * half + 127) / 128, 128, 0, s>>>(t, freqs, out, B, half);
+  launch_pdl(time_sinusoid_kernel, dim3((B * half + 127) / 128), dim3(128), 0, s, t, freqs, out, B, half);
 }
 
 // test helpers: fp32 = hi + lo, and [rows, C] -> transposed split [C, rows] per image
@@ -456,6 +466,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
                                                            const float* __restrict__ bias,
                                                            float* __restrict__ out, long long ld_out,
                                                            int B, int N, int K, int out_act) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_in[16][33];
   __shared__ float s_w[16][33];
   const int tn = threadIdx.x & 15, tb = threadIdx.x >> 4;
@@ -486,7 +498,7 @@ void launch_small_linear(const float* in, long long ld_in, const float* W, const
                          float* out, long long ld_out, int B, int N, int K, int out_act,
                          cudaStream_t s) {
   dim3 grid((N + 15) / 16, (B + 15) / 16);
-  small_linear_kernel<<<grid, 256, 0, s>>>(in, ld_in, W, bias, out, ld_out, B, N, K, out_act);
+  launch_pdl(small_linear_kernel, grid, dim3(256), 0, s, in, ld_in, W, bias, out, ld_out, B, N, K, out_act);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -501,6 +513,8 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__
                                                        const float* __restrict__ bias,
                                                        float* __restrict__ out, int H, int W, int C,
                                                        int Cout) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int pitch = C + 4;
   float* st = sm;                                        // [(T+2)*(T+2)][pitch]
@@ -606,7 +620,7 @@ void launch_conv_out(const float* h, const double* stats, const float* gamma, co
     attr_set = true;
   }
   dim3 grid((W + CO_T - 1) / CO_T, (H + CO_T - 1) / CO_T, B);
-  conv_out_kernel<<<grid, 256, smem, s>>>(h, stats, gamma, beta, eps, w, bias, out, H, W, C, Cout);
+  launch_pdl(conv_out_kernel, grid, dim3(256), smem, s, h, stats, gamma, beta, eps, w, bias, out, H, W, C, Cout);
 }
 
 // ------------------------------------------------------------------------------------------------
