@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Dict, Tuple
 
 import torch
@@ -24,7 +25,11 @@ class UNetEngine:
         self.device = None
         self._stamp = None
         self._workspaces: Dict[Tuple[int, int, int, int], torch.Tensor] = {}
+        self._graphs: Dict[Tuple[int, int, int, int], tuple] = {}
         self._keep = []
+        # replay each (batch, n_cond, H, W) evaluation as a CUDA graph (measured ~3 % faster than the
+        # 261 individual launches); PF_CUDA_GRAPH=0 disables it
+        self.use_graph = os.environ.get("PF_CUDA_GRAPH", "1") != "0"
 
     # ------------------------------------------------------------------ handle management
     def _create(self, device: torch.device) -> None:
@@ -79,12 +84,14 @@ class UNetEngine:
         del keep
         self._stamp = stamp
         self._workspaces.clear()
+        self._graphs.clear()
 
     def close(self) -> None:
         if self.handle.value is not None:
             lib().pf_unet_destroy(self.handle)
             self.handle = ctypes.c_void_p()
         self._workspaces.clear()
+        self._graphs.clear()
         self._stamp = None
 
     def __del__(self):
@@ -113,6 +120,37 @@ class UNetEngine:
         cond = cond.to(dev).contiguous().float()
         t = t.to(device=dev, dtype=torch.int64).contiguous()
         key = (B, n_cond, H, W)
+        if self.use_graph and profile is None and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graph(key, x, t, cond, out)
+        return self._forward_eager(key, x, t, cond, out, profile)
+
+    def _forward_graph(self, key, x, t, cond, out):
+        entry = self._graphs.get(key)
+        if entry is None:
+            # static buffers + one eager call (builds the plan) + capture
+            xs, ts, cs = x.clone(), t.clone(), cond.clone()
+            os_ = torch.empty((key[0], self.cfg["out_channels"], key[2], key[3]), dtype=torch.float32,
+                              device=x.device)
+            self._forward_eager(key, xs, ts, cs, os_, None)
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._forward_eager(key, xs, ts, cs, os_, None)
+            entry = (graph, xs, ts, cs, os_)
+            self._graphs[key] = entry
+        graph, xs, ts, cs, os_ = entry
+        xs.copy_(x)
+        ts.copy_(t)
+        cs.copy_(cond)
+        graph.replay()
+        if out is None:
+            return os_.clone()
+        out.copy_(os_)
+        return out
+
+    def _forward_eager(self, key, x, t, cond, out, profile):
+        B, n_cond, H, W = key
+        dev = x.device
         with torch.cuda.device(dev):
             ws = self._workspaces.get(key)
             if ws is None:
