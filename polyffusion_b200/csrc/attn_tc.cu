@@ -5,14 +5,18 @@
 //
 // One CTA handles 128 query rows of one (sample, head) at a time (persistent over work items) and
 // walks the keys in blocks of 64 TWICE:
-//   pass 1:  S_j = Q K_j^T            -> running row maximum m            (no rescaling later)
-//   pass 2:  S_j again, P_j = exp2((S_j - m) * scale*log2e), l += rowsum(P_j), O += P_j V_j
-// and finally O / l.  Recomputing S costs 50% more MMA work on 6% of the network's FLOPs and removes
-// the accumulator-rescaling path of online softmax entirely.
+//   pass 1:  S~_j = Q_hi K_hi_j^T     -> running row maximum m~           (no rescaling later)
+//   pass 2:  S_j in full precision, P_j = exp2((S_j - m~) * scale*log2e), l += rowsum(P_j), O += P_j V_j
+// and finally O / l.  softmax is invariant to the shift, so pass 1 only needs a stabiliser close to
+// the true maximum: ONE bf16 product (hi*hi, K_lo is not even loaded) instead of three.  Pass 2 and
+// P V use the stacked-operand form of the split product (see gemm_tc.cu):
+//   Q_hi x [K_hi ; K_lo] (N = 128)  +  Q_lo x K_hi (N = 64, accumulated onto columns [0, 64))
+// so an S / O accumulator is 128 columns wide and the consumer adds its two halves.  Recomputing S
+// removes the accumulator-rescaling path of online softmax entirely.
 //
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..9 =
 // softmax / epilogue (two warps per TMEM lane quarter, 32 key columns each).
-// TMEM: S double buffer (2 x 64 cols) + O (64 cols).  smem: Q, K ring, V^T ring, P double buffer
+// TMEM: S double buffer (2 x 128 cols) + O (128 cols).  smem: Q, K ring, V^T ring, P double buffer
 // (written by the softmax warps in the UMMA K-major 128B-swizzled layout, consumed as the A operand).
 #include "common.cuh"
 #include "attn_tc.cuh"
@@ -45,7 +49,9 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
   __shared__ uint32_t tmem_base_s;
 
   constexpr uint32_t IDESC = umma_idesc_bf16(64);
-  constexpr int TMEM_COLS = 256;  // S0 [0,64) S1 [64,128) O [128,192)
+  constexpr uint32_t IDESC2 = umma_idesc_bf16(128);
+  constexpr int TMEM_COLS = 512;  // S0 [0,128) S1 [128,256) O [256,384)
+  constexpr uint32_t O_COL = 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -102,11 +108,12 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
             {
               const uint32_t st = kc % AT_KS, ph = (kc / AT_KS) & 1u;
               mbar_wait(smem_u32(&k_empty[st]), ph ^ 1u);
-              mbar_expect_tx(smem_u32(&k_full[st]), 2 * AT_KV_BYTES);
+              mbar_expect_tx(smem_u32(&k_full[st]), (pass == 1 ? 2 : 1) * AT_KV_BYTES);
               const uint32_t dst = base + AT_OFF_K + st * 2 * AT_KV_BYTES;
               tma_load_2d(dst, &p.k_hi, smem_u32(&k_full[st]), p.kcol0 + h * 64, b * p.Nk + j * 64);
-              tma_load_2d(dst + AT_KV_BYTES, &p.k_lo, smem_u32(&k_full[st]), p.kcol0 + h * 64,
-                          b * p.Nk + j * 64);
+              if (pass == 1)
+                tma_load_2d(dst + AT_KV_BYTES, &p.k_lo, smem_u32(&k_full[st]), p.kcol0 + h * 64,
+                            b * p.Nk + j * 64);
               ++kc;
             }
             if (pass == 1) {
@@ -128,21 +135,24 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
       uint32_t kc = 0, vc = 0, sc = 0, pc = 0, it = 0;
       const uint64_t dq_hi = umma_desc_sw128(base + AT_OFF_Q);
       const uint64_t dq_lo = umma_desc_sw128(base + AT_OFF_Q + AT_Q_BYTES);
-      auto issue_s = [&]() {
+      auto issue_s = [&](bool full) {
         const uint32_t st = kc % AT_KS, kph = (kc / AT_KS) & 1u;
         const uint32_t sb = sc & 1u, sph = (sc >> 1) & 1u;
         mbar_wait(smem_u32(&k_full[st]), kph);
         mbar_wait(smem_u32(&s_empty[sb]), sph ^ 1u);
         tc_fence_after();
+        // K_hi (64 rows) is followed by K_lo (64 rows) in the stage: one 128-row B operand
         const uint64_t dk_hi = umma_desc_sw128(base + AT_OFF_K + st * 2 * AT_KV_BYTES);
-        const uint64_t dk_lo = umma_desc_sw128(base + AT_OFF_K + st * 2 * AT_KV_BYTES + AT_KV_BYTES);
-        const uint32_t acc = tmem_base + sb * 64;
+        const uint32_t acc = tmem_base + sb * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t ko = static_cast<uint64_t>(k * 2);
-          umma_bf16(acc, dq_lo + ko, dk_hi + ko, IDESC, k != 0);
-          umma_bf16(acc, dq_hi + ko, dk_lo + ko, IDESC, 1u);
-          umma_bf16(acc, dq_hi + ko, dk_hi + ko, IDESC, 1u);
+          if (full) {
+            umma_bf16(acc, dq_hi + ko, dk_hi + ko, IDESC2, k != 0);
+            umma_bf16(acc, dq_lo + ko, dk_hi + ko, IDESC, 1u);
+          } else {
+            umma_bf16(acc, dq_hi + ko, dk_hi + ko, IDESC, k != 0);
+          }
         }
         umma_commit(smem_u32(&k_empty[st]));
         umma_commit(smem_u32(&s_full[sb]));
@@ -152,10 +162,10 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
       for (long long w = blockIdx.x; w < items; w += gridDim.x, ++it) {
         mbar_wait(smem_u32(&q_full), it & 1u);
         tc_fence_after();
-        for (int j = 0; j < nb; ++j) issue_s();  // pass 1
-        issue_s();                               // pass 2, block 0
+        for (int j = 0; j < nb; ++j) issue_s(false);  // pass 1
+        issue_s(true);                                // pass 2, block 0
         for (int j = 0; j < nb; ++j) {
-          if (j + 1 < nb) issue_s();
+          if (j + 1 < nb) issue_s(true);
           const uint32_t pb = pc & 1u, pph = (pc >> 1) & 1u;
           const uint32_t st = vc % AT_VS, vph = (vc / AT_VS) & 1u;
           mbar_wait(smem_u32(&p_full[pb]), pph);
@@ -164,15 +174,14 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
           tc_fence_after();
           const uint64_t dp_hi = umma_desc_sw128(base + AT_OFF_P + pb * 2 * AT_P_BYTES);
           const uint64_t dp_lo = umma_desc_sw128(base + AT_OFF_P + pb * 2 * AT_P_BYTES + AT_P_BYTES);
+          // V^T_hi (64 rows = d) followed by V^T_lo: one 128-row B operand
           const uint64_t dv_hi = umma_desc_sw128(base + AT_OFF_V + st * 2 * AT_KV_BYTES);
-          const uint64_t dv_lo = umma_desc_sw128(base + AT_OFF_V + st * 2 * AT_KV_BYTES + AT_KV_BYTES);
-          const uint32_t acc = tmem_base + 128;
+          const uint32_t acc = tmem_base + O_COL;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ko = static_cast<uint64_t>(k * 2);
-            umma_bf16(acc, dp_lo + ko, dv_hi + ko, IDESC, (j | k) != 0);
-            umma_bf16(acc, dp_hi + ko, dv_lo + ko, IDESC, 1u);
-            umma_bf16(acc, dp_hi + ko, dv_hi + ko, IDESC, 1u);
+            umma_bf16(acc, dp_hi + ko, dv_hi + ko, IDESC2, (j | k) != 0);
+            umma_bf16(acc, dp_lo + ko, dv_hi + ko, IDESC, 1u);
           }
           umma_commit(smem_u32(&p_empty[pb]));
           umma_commit(smem_u32(&v_empty[st]));
@@ -203,7 +212,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
         mbar_wait(smem_u32(&s_full[sb]), sph);
         tc_fence_after();
         uint32_t v[32];
-        tmem_ld32(lane_addr + sb * 64 + half * 32, v);
+        tmem_ld32(lane_addr + sb * 128 + half * 32, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -222,8 +231,9 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
         const uint32_t pb = pc & 1u, pph = (pc >> 1) & 1u;
         mbar_wait(smem_u32(&s_full[sb]), sph);
         tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(lane_addr + sb * 64 + half * 32, v);
+        uint32_t v[32], v2[32];
+        tmem_ld32(lane_addr + sb * 128 + half * 32, v);
+        tmem_ld32(lane_addr + sb * 128 + 64 + half * 32, v2);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -231,8 +241,10 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
         uint32_t ph[16], pl[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_ex2(fmaf(__uint_as_float(v[2 * i]), c, -mc));
-          const float p1 = fast_ex2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
+          const float s0 = __uint_as_float(v[2 * i]) + __uint_as_float(v2[2 * i]);
+          const float s1 = __uint_as_float(v[2 * i + 1]) + __uint_as_float(v2[2 * i + 1]);
+          const float p0 = fast_ex2(fmaf(s0, c, -mc));
+          const float p1 = fast_ex2(fmaf(s1, c, -mc));
           sum += p0 + p1;
           split2(p0, p1, ph[i], pl[i]);
         }
@@ -256,8 +268,14 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
       mbar_wait(smem_u32(&o_full), it & 1u);
       tc_fence_after();
       uint32_t o[32];
-      tmem_ld32(lane_addr + 128 + half * 32, o);
-      tmem_ld_wait();
+      {
+        uint32_t o2[32];
+        tmem_ld32(lane_addr + O_COL + half * 32, o);
+        tmem_ld32(lane_addr + O_COL + 64 + half * 32, o2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) + __uint_as_float(o2[i]));
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&o_empty));

@@ -46,8 +46,19 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, long long 
 // MODE / STATS are compile-time so that every kernel carries only ONE epilogue variant: the fully
 // general kernel was ~100 KB of SASS and the short (K = 256) launches stalled on instruction fetch
 // (ncu: 35 % of samples `stall_no_inst`).
-template <int BN, bool TWO, int MODE, bool STATS>
+//
+// STACK (cta_group::2, BN <= 128): the three products are issued as TWO instructions per K = 16 step,
+//   A_hi x [B_hi ; B_lo]   (N = 2 BN: each CTA's B rows are its B_hi half followed by its B_lo half,
+//                           which already sit back to back in the stage)
+//   A_lo x  B_hi           (N = BN, accumulated BN/2 columns further right)
+// so A_hi and B_hi are read from shared memory once instead of twice (15 -> 11 KB per step per CTA
+// at BN = 64, 18 -> 14 KB at BN = 128; TMA fills and UMMA operand reads share the same 128 B/clk).
+// The accumulator of a tile is then 2 BN columns wide,
+//   [0, h) hi*hi (n < h) | [h, BN) hi*lo + lo*hi (n < h) | [BN, BN+h) hi*hi + lo*hi (n >= h) | [BN+h, 2BN) hi*lo (n >= h)
+// with h = BN / 2, and the epilogue adds the two pieces of every output column.
+template <int BN, bool TWO, int MODE, bool STATS, bool STACK>
 __device__ __forceinline__ void gemm_body(const GemmParams& p) {
+  static_assert(!STACK || (TWO && BN <= 128), "stacked B operand needs cta_group::2 and 4*BN <= 512 TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -59,7 +70,9 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   constexpr int B_BYTES = (TWO ? BN / 2 : BN) * 128;  // B rows staged by this CTA
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   constexpr uint32_t IDESC = TWO ? umma_idesc_bf16_m256(BN) : umma_idesc_bf16(BN);
-  constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: power of two >= 32
+  constexpr uint32_t IDESC_2N = umma_idesc_bf16_m256(STACK ? 2 * BN : BN);
+  constexpr int ACC_COLS = STACK ? 2 * BN : BN;  // TMEM columns of one accumulator stage
+  constexpr int TMEM_COLS = 2 * ACC_COLS;        // 128 / 256 / 512: power of two >= 32
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0);
   // tile walk: 1-CTA: tile t of this CTA; 2-CTA: pair-tile t of this cluster, my m-tile = 2*pair + rank
@@ -163,7 +176,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1u);
         tc_fence_after();
-        const uint32_t acc = tmem_base + static_cast<uint32_t>(as * BN);
+        const uint32_t acc = tmem_base + static_cast<uint32_t>(as * ACC_COLS);
         for (int kbi = 0; kbi < nkb; ++kbi, ++it) {
           const int stage = it % nstages;
           const uint32_t ph = static_cast<uint32_t>(it / nstages) & 1u;
@@ -177,7 +190,10 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t ko = static_cast<uint64_t>(k * 2);  // 32 B per K=16 step (16 B units)
-            if (TWO) {
+            if (STACK) {
+              umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC_2N, (kbi | k) != 0);
+              umma2_bf16(acc + BN / 2, da_lo + ko, db_hi + ko, IDESC, 1u);
+            } else if (TWO) {
               umma2_bf16(acc, da_lo + ko, db_hi + ko, IDESC, (kbi | k) != 0);
               umma2_bf16(acc, da_hi + ko, db_lo + ko, IDESC, 1u);
               umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC, 1u);
@@ -244,7 +260,23 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
       tc_fence_after();
       const uint32_t taddr =
-          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * ACC_COLS);
+      // logical accumulator columns [c, c + 32) of this warp's 32 rows (wait included)
+      auto ld_acc = [&](int c, uint32_t (&v)[32]) {
+        if constexpr (STACK) {
+          constexpr int h = BN / 2;
+          const int ca = (c / h) * BN + (c % h);
+          uint32_t w[32];
+          tmem_ld32(taddr + ca, v);
+          tmem_ld32(taddr + ca + h, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        } else {
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+        }
+      };
 
       if constexpr (MODE == OUT_SPLIT_T) {
         // [img][n][token]; consecutive lanes -> consecutive tokens (already coalesced)
@@ -253,8 +285,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
 #pragma unroll 1
         for (int c = chalf * 32; c < BN; c += 64) {
           uint32_t v[32];
-          tmem_ld32(taddr + c, v);
-          tmem_ld_wait();
+          ld_acc(c, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             __nv_bfloat16 h, l;
@@ -284,11 +315,10 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           }
           {
             uint32_t v[32];
-            tmem_ld32(taddr + c, v);
+            ld_acc(c, v);
             if constexpr (geglu) {
               uint32_t g[32];
-              tmem_ld32(taddr + BN / 2 + c, g);
-              tmem_ld_wait();
+              ld_acc(BN / 2 + c, g);
               // value = cols [ocol0 + c, +32) of the first half, gate = same cols of the second
               // half of the (un-interleaved) projection: out = (x + b_x) * gelu(g + b_g)
               const float4* bx = reinterpret_cast<const float4*>(av + ocol0 + c);
@@ -305,7 +335,6 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 }
               }
             } else {
-              tmem_ld_wait();
               if (av) {
                 const float4* b4 = reinterpret_cast<const float4*>(av + tc.n0 + c);
 #pragma unroll
@@ -423,21 +452,37 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
 
 template <int BN, int MODE, bool STATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  gemm_body<BN, false, MODE, STATS>(p);
+  gemm_body<BN, false, MODE, STATS, false>(p);
 }
 
 template <int BN, int MODE, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
-  gemm_body<BN, true, MODE, STATS>(p);
+  gemm_body<BN, true, MODE, STATS, false>(p);
+}
+
+// cta_group::2 with the stacked [B_hi ; B_lo] operand (BN <= 128)
+template <int BN, int MODE, bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc2s_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, true, MODE, STATS, true>(p);
 }
 
 typedef void (*GemmKernel)(GemmParams);
 
 // variant index: 0 = fp32, 1 = fp32 + GroupNorm statistics, 2 = split, 3 = split transposed, 4 = GeGLU
-template <int BN, bool TWO>
+// kind: 0 = one CTA per tile, 1 = cta_group::2, 2 = cta_group::2 with stacked B (BN <= 128)
+template <int BN, int KIND>
 static GemmKernel pick_variant(int v) {
-  if (TWO) {
+  if constexpr (KIND == 2) {
+    switch (v) {
+      case 0: return gemm_tc2s_kernel<BN, OUT_F32, false>;
+      case 1: return gemm_tc2s_kernel<BN, OUT_F32, true>;
+      case 2: return gemm_tc2s_kernel<BN, OUT_SPLIT, false>;
+      case 3: return gemm_tc2s_kernel<BN, OUT_SPLIT_T, false>;
+      default: return gemm_tc2s_kernel<BN, OUT_GEGLU, false>;
+    }
+  } else if constexpr (KIND == 1) {
     switch (v) {
       case 0: return gemm_tc2_kernel<BN, OUT_F32, false>;
       case 1: return gemm_tc2_kernel<BN, OUT_F32, true>;
@@ -445,30 +490,33 @@ static GemmKernel pick_variant(int v) {
       case 3: return gemm_tc2_kernel<BN, OUT_SPLIT_T, false>;
       default: return gemm_tc2_kernel<BN, OUT_GEGLU, false>;
     }
-  }
-  switch (v) {
-    case 0: return gemm_tc_kernel<BN, OUT_F32, false>;
-    case 1: return gemm_tc_kernel<BN, OUT_F32, true>;
-    case 2: return gemm_tc_kernel<BN, OUT_SPLIT, false>;
-    case 3: return gemm_tc_kernel<BN, OUT_SPLIT_T, false>;
-    default: return gemm_tc_kernel<BN, OUT_GEGLU, false>;
+  } else {
+    switch (v) {
+      case 0: return gemm_tc_kernel<BN, OUT_F32, false>;
+      case 1: return gemm_tc_kernel<BN, OUT_F32, true>;
+      case 2: return gemm_tc_kernel<BN, OUT_SPLIT, false>;
+      case 3: return gemm_tc_kernel<BN, OUT_SPLIT_T, false>;
+      default: return gemm_tc_kernel<BN, OUT_GEGLU, false>;
+    }
   }
 }
 
-static GemmKernel pick_kernel(int bn, bool two, int v) {
+static GemmKernel pick_kernel(int bn, int kind, int v) {
   switch (bn) {
-    case 64: return two ? pick_variant<64, true>(v) : pick_variant<64, false>(v);
-    case 128: return two ? pick_variant<128, true>(v) : pick_variant<128, false>(v);
-    case 256: return two ? pick_variant<256, true>(v) : pick_variant<256, false>(v);
+    case 64: return kind == 2 ? pick_variant<64, 2>(v) : kind == 1 ? pick_variant<64, 1>(v) : pick_variant<64, 0>(v);
+    case 128: return kind == 2 ? pick_variant<128, 2>(v) : kind == 1 ? pick_variant<128, 1>(v) : pick_variant<128, 0>(v);
+    case 256: return kind == 2 ? nullptr : kind == 1 ? pick_variant<256, 1>(v) : pick_variant<256, 0>(v);
     default: return nullptr;
   }
 }
 
 cudaError_t gemm_init_attrs() {
   for (int bn : {64, 128, 256})
-    for (int two = 0; two < 2; ++two)
+    for (int kind = 0; kind < 3; ++kind)
       for (int v = 0; v < 5; ++v) {
-        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_kernel(bn, two != 0, v)),
+        GemmKernel k = pick_kernel(bn, kind, v);
+        if (!k) continue;
+        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k),
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
       }
@@ -483,7 +531,8 @@ cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t 
     case OUT_SPLIT_T: v = 3; break;
     default: v = 4; break;
   }
-  GemmKernel k = pick_kernel(bn, p.two_cta != 0, v);
+  const int kind = p.two_cta ? ((p.stack && bn <= 128) ? 2 : 1) : 0;
+  GemmKernel k = pick_kernel(bn, kind, v);
   if (!k) return cudaErrorInvalidValue;
   if (p.two_cta) {
     const int smem = p.nstages * gemm_stage_bytes2(bn) + 1024 + gemm_epilogue_smem_bytes(bn);

@@ -63,6 +63,7 @@ struct alignas(64) GemmParams {
   long long stats_ld;
   int geglu_f;          // OUT_GEGLU: number of output features F (bias layout [x: F | gate: F])
   int two_cta;          // 1: cta_group::2 kernel (tile pairs; B maps have boxes of BN/2 rows)
+  int stack;            // 1 (with two_cta, BN <= 128): stacked [B_hi ; B_lo] operand, 2 MMAs per K step
   // nearest-2x-upsample + conv3x3 evaluated as four 2x2 parity convolutions at LOW resolution:
   // OUT_F32 rows are scattered to pixel (2y + up_py, 2x + up_px) of the [img][2H][2W] output
   int up_mode, up_py, up_px;

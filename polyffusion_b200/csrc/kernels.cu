@@ -78,11 +78,97 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   }
 }
 
-void launch_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int Cin,
-                    int H, int W, int Cout, cudaStream_t s) {
+// Fast path for the prmat2c geometry (Cin = 2, Cout = 64, W <= 128): a thread owns 4 output channels
+// (its 72 weights live in registers) and walks pixels; a warp = 2 adjacent pixels x 16 channel quads,
+// so every store instruction writes 512 contiguous bytes and the only shared-memory traffic is the
+// 18 broadcast halo reads per pixel.  The GroupNorm statistics of the output (needed by the first
+// ResBlock and by the last skip connection) are reduced here as well instead of a separate pass.
+// Accumulation order (ci, ky, kx) is the same as in conv_in_kernel.
+constexpr int CI2_ROWS = 4;
+__global__ void __launch_bounds__(256) conv_in2_kernel(const float* __restrict__ x,
+                                                       const float* __restrict__ w,
+                                                       const float* __restrict__ bias,
+                                                       float* __restrict__ out,
+                                                       double* __restrict__ stats, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int HR = CI2_ROWS + 2, PITCH = 132;
+  __shared__ float sx[2 * HR * PITCH];
+  __shared__ float s_red[2][16][64];
+  const int b = blockIdx.y, y0 = blockIdx.x * CI2_ROWS;
+  const int cq = threadIdx.x & 15, ps = threadIdx.x >> 4;
+  for (int i = threadIdx.x; i < 2 * HR * PITCH; i += 256) {
+    const int ci = i / (HR * PITCH), r = (i / PITCH) % HR, xx = i % PITCH;
+    const int gy = y0 + r - 1, gx = xx - 1;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __ldg(x + ((static_cast<long long>(b) * 2 + ci) * H + gy) * W + gx);
+    sx[i] = v;
+  }
+  float4 wr[18];
+#pragma unroll
+  for (int k = 0; k < 18; ++k) {  // k = ci * 9 + ky * 3 + kx; w is [64][2][3][3]
+    wr[k].x = __ldg(w + (4 * cq + 0) * 18 + k);
+    wr[k].y = __ldg(w + (4 * cq + 1) * 18 + k);
+    wr[k].z = __ldg(w + (4 * cq + 2) * 18 + k);
+    wr[k].w = __ldg(w + (4 * cq + 3) * 18 + k);
+  }
+  const float4 bv = *reinterpret_cast<const float4*>(bias + 4 * cq);
+  __syncthreads();
+  float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;
+  for (int rr = 0; rr < CI2_ROWS; ++rr) {
+    const int y = y0 + rr;
+    if (y >= H) break;
+    for (int px = ps; px < W; px += 16) {
+      float4 acc = bv;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float v = sx[(ci * HR + rr + r) * PITCH + px + kx];
+            const float4 ww = wr[ci * 9 + r * 3 + kx];
+            acc.x = fmaf(v, ww.x, acc.x);
+            acc.y = fmaf(v, ww.y, acc.y);
+            acc.z = fmaf(v, ww.z, acc.z);
+            acc.w = fmaf(v, ww.w, acc.w);
+          }
+      *reinterpret_cast<float4*>(out + ((static_cast<long long>(b) * H + y) * W + px) * 64 + 4 * cq) = acc;
+      ssum.x += acc.x; ssum.y += acc.y; ssum.z += acc.z; ssum.w += acc.w;
+      ssq.x = fmaf(acc.x, acc.x, ssq.x); ssq.y = fmaf(acc.y, acc.y, ssq.y);
+      ssq.z = fmaf(acc.z, acc.z, ssq.z); ssq.w = fmaf(acc.w, acc.w, ssq.w);
+    }
+  }
+  if (stats) {
+    *reinterpret_cast<float4*>(&s_red[0][ps][4 * cq]) = ssum;
+    *reinterpret_cast<float4*>(&s_red[1][ps][4 * cq]) = ssq;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+      double t = 0.0;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) t += static_cast<double>(s_red[which][r][c]);
+      atomicAdd(stats + (static_cast<long long>(b) * 64 + c) * 2 + which, t);
+    }
+  }
+}
+
+void launch_gn_stats(const float* src, double* acc, int B, int HW, int Cs, int Ctot, int coff,
+                     cudaStream_t s);
+
+void launch_conv_in(const float* x, const float* w, const float* bias, float* out, double* stats, int B,
+                    int Cin, int H, int W, int Cout, cudaStream_t s) {
+  static const bool slow = std::getenv("PF_CONV_SLOW") != nullptr;  // A/B switch: generic kernels
+  if (!slow && Cin == 2 && Cout == 64 && W <= 128) {
+    dim3 grid((H + CI2_ROWS - 1) / CI2_ROWS, B);
+    launch_pdl(conv_in2_kernel, grid, dim3(256), 0, s, x, w, bias, out, stats, H, W);
+    return;
+  }
   dim3 grid((W + 63) / 64, (H + CI_ROWS - 1) / CI_ROWS, B);
   const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + Cin * (CI_ROWS + 2) * 66) * sizeof(float);
   launch_pdl(conv_in_kernel, grid, dim3(256), smem, s, x, w, bias, out, Cin, H, W, Cout);
+  if (stats) launch_gn_stats(out, stats, B, H * W, Cout, Cout, 0, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,6 +554,12 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
                                                            int B, int N, int K, int out_act) {
   pdl_wait();
   pdl_trigger();
+  // blockIdx.z = group g: independent problems laid side by side (in += g*K, W += g*N*K,
+  // bias += g*N, out += g*N); a plain call has one group
+  in += static_cast<long long>(blockIdx.z) * K;
+  W += static_cast<long long>(blockIdx.z) * N * K;
+  if (bias) bias += static_cast<long long>(blockIdx.z) * N;
+  out += static_cast<long long>(blockIdx.z) * N;
   __shared__ float s_in[16][33];
   __shared__ float s_w[16][33];
   const int tn = threadIdx.x & 15, tb = threadIdx.x >> 4;
@@ -496,8 +588,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 }
 void launch_small_linear(const float* in, long long ld_in, const float* W, const float* bias,
                          float* out, long long ld_out, int B, int N, int K, int out_act,
-                         cudaStream_t s) {
-  dim3 grid((N + 15) / 16, (B + 15) / 16);
+                         cudaStream_t s, int groups) {
+  dim3 grid((N + 15) / 16, (B + 15) / 16, groups);
   launch_pdl(small_linear_kernel, grid, dim3(256), 0, s, in, ld_in, W, bias, out, ld_out, B, N, K, out_act);
 }
 
@@ -609,16 +701,136 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__
       out[((static_cast<long long>(b) * Cout + co) * H + gy) * W + gx] = acc[co] + bias[co];
 }
 
+// Fast path (C = 64, Cout = 2, W <= 128): scatter form.  The halo-tile kernel above reads every
+// activated input value 9 times from shared memory (one LDS.128 per 8 FMAs: shared-memory bound,
+// 370 us at batch 64).  Here a block walks the input rows of a 16-row strip once; each activated
+// pixel is read ONCE and turned into its 9 x 2 tap partials  part[tap][co] = sum_c v[c] w[co][c][tap],
+// kept for three rows in a ring; output row y then gathers 9 partials per (x, co):
+//   out[y][x][co] = bias[co] + sum_{ky,kx} part(row y+ky-1)[ky*3+kx][co][x+kx-1].
+// thread = (x, co); the weights are warp-uniform (broadcast LDS.128), pixel reads are conflict-free
+// (pitch 68 floats).
+constexpr int CO2_ROWS = 16, CO2_PITCH = 68, CO2_PW = 130;
+constexpr int CO2_SMEM = (128 * CO2_PITCH + 3 * 9 * 2 * CO2_PW + 2 * 9 * 64 + 128) * 4;
+__global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict__ h,
+                                                        const double* __restrict__ stats,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        const float* __restrict__ w,
+                                                        const float* __restrict__ bias,
+                                                        float* __restrict__ out, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sm[];
+  float* st = sm;                          // [128][68] activated input row
+  float* part = st + 128 * CO2_PITCH;      // [3][9][2][130]
+  float* sw = part + 3 * 9 * 2 * CO2_PW;   // [2][9][64]
+  float* sc = sw + 2 * 9 * 64;             // [64] scale, [64] shift
+  float* sh = sc + 64;
+  const int b = blockIdx.y, y0 = blockIdx.x * CO2_ROWS;
+  const int y1 = min(H, y0 + CO2_ROWS);
+  if (threadIdx.x < 64) {
+    // GroupNorm(32, 64): 2 channels per group, from the producer's per-(sample, channel) fp64 sums
+    const int c = threadIdx.x, g = c >> 1;
+    const double* a = stats + (static_cast<long long>(b) * 64 + g * 2) * 2;
+    const double ts = a[0] + a[2], tq = a[1] + a[3];
+    const double n = static_cast<double>(H) * W * 2;
+    const double mean = ts / n;
+    double var = tq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float s1 = gamma[c] * rstd;
+    sc[c] = s1;
+    sh[c] = beta[c] - static_cast<float>(mean) * s1;
+  }
+  for (int i = threadIdx.x; i < 2 * 9 * 64; i += 256) {
+    // w [2][64][3][3] -> sw[co][tap][c]
+    const int co = i / 576, r = i % 576, tap = r >> 6, c = r & 63;
+    sw[i] = __ldg(w + (co * 64 + c) * 9 + tap);
+  }
+  for (int i = threadIdx.x; i < 3 * 9 * 2 * CO2_PW; i += 256) part[i] = 0.f;  // incl. the x = -1 / W columns
+  __syncthreads();
+  const int x = threadIdx.x & 127, co = threadIdx.x >> 7;
+  const float bco = __ldg(bias + co);
+  for (int r = y0 - 1; r <= y1; ++r) {
+    const int slot = (r + 3) % 3;
+    const bool inside = (r >= 0 && r < H);
+    if (inside) {
+      const float4* src = reinterpret_cast<const float4*>(h + (static_cast<long long>(b) * H + r) * W * 64);
+      float4 a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = threadIdx.x + 256 * u;
+        a[u] = (idx < W * 16) ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = threadIdx.x + 256 * u;
+        const int pix = idx >> 4, c = (idx & 15) * 4;
+        float4 v;
+        v.x = silu_fast(fmaf(a[u].x, sc[c + 0], sh[c + 0]));
+        v.y = silu_fast(fmaf(a[u].y, sc[c + 1], sh[c + 1]));
+        v.z = silu_fast(fmaf(a[u].z, sc[c + 2], sh[c + 2]));
+        v.w = silu_fast(fmaf(a[u].w, sc[c + 3], sh[c + 3]));
+        *reinterpret_cast<float4*>(st + pix * CO2_PITCH + c) = v;
+      }
+    }
+    __syncthreads();
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    if (inside && x < W) {
+      const float* ip = st + x * CO2_PITCH;
+      const float* wp = sw + co * 576;
+#pragma unroll 4
+      for (int c = 0; c < 64; c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(ip + c);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 ww = *reinterpret_cast<const float4*>(wp + t * 64 + c);
+          acc[t] = fmaf(v.x, ww.x, acc[t]);
+          acc[t] = fmaf(v.y, ww.y, acc[t]);
+          acc[t] = fmaf(v.z, ww.z, acc[t]);
+          acc[t] = fmaf(v.w, ww.w, acc[t]);
+        }
+      }
+    }
+    if (x < W) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) part[((slot * 9 + t) * 2 + co) * CO2_PW + x + 1] = acc[t];
+    }
+    __syncthreads();
+    const int y = r - 1;
+    if (y >= y0 && y < y1 && x < W) {
+      float sum = bco;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int sl = (y + ky - 1 + 3) % 3;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+          sum += part[((sl * 9 + ky * 3 + kx) * 2 + co) * CO2_PW + x + kx];
+      }
+      out[((static_cast<long long>(b) * 2 + co) * H + y) * W + x] = sum;
+    }
+  }
+}
+
 void launch_conv_out(const float* h, const double* stats, const float* gamma, const float* beta,
                      float eps, const float* w, const float* bias, float* out, int B, int H, int W,
                      int C, int Cout, cudaStream_t s) {
   static bool attr_set = false;
-  const size_t smem = (static_cast<size_t>(CO_T + 2) * (CO_T + 2) * (C + 4) +
-                       static_cast<size_t>(Cout) * 9 * C + 2 * C) * sizeof(float);
   if (!attr_set) {
     cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_out2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CO2_SMEM);
     attr_set = true;
   }
+  static const bool slow = std::getenv("PF_CONV_SLOW") != nullptr;
+  if (!slow && C == 64 && Cout == 2 && W <= 128) {
+    dim3 grid((H + CO2_ROWS - 1) / CO2_ROWS, B);
+    launch_pdl(conv_out2_kernel, grid, dim3(256), CO2_SMEM, s, h, stats, gamma, beta, eps, w, bias, out, H, W);
+    return;
+  }
+  const size_t smem = (static_cast<size_t>(CO_T + 2) * (CO_T + 2) * (C + 4) +
+                       static_cast<size_t>(Cout) * 9 * C + 2 * C) * sizeof(float);
   dim3 grid((W + CO_T - 1) / CO_T, (H + CO_T - 1) / CO_T, B);
   launch_pdl(conv_out_kernel, grid, dim3(256), smem, s, h, stats, gamma, beta, eps, w, bias, out, H, W, C, Cout);
 }

@@ -12,9 +12,11 @@ namespace pf {
 
 typedef __nv_bfloat16 bf16;
 
-// x NCHW [B,Cin,H,W] -> out NHWC [B,H,W,Cout], 3x3 pad 1, fp32 (unet.py:79 first conv)
-void launch_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int Cin,
-                    int H, int W, int Cout, cudaStream_t s);
+// x NCHW [B,Cin,H,W] -> out NHWC [B,H,W,Cout], 3x3 pad 1, fp32 (unet.py:79 first conv); stats
+// (optional, zero-initialised [B][Cout][2] fp64) receives the per-(sample, channel) sum / sum of
+// squares of the output (GroupNorm statistics for its consumers)
+void launch_conv_in(const float* x, const float* w, const float* bias, float* out, double* stats, int B,
+                    int Cin, int H, int W, int Cout, cudaStream_t s);
 
 // per-(sample, channel) sum / sum-of-squares (fp64 atomics) of an NHWC tensor [B,HW,Cs] written at
 // channel offset coff of acc [B, Ctot, 2]  (only used for the first conv's output; every other
@@ -59,7 +61,7 @@ void launch_transpose_split(const float* src, bf16* hi, bf16* lo, int imgs, int 
 // out[b, n] = act(W[n,:] . in[b,:] + bias[n]); out_act: 0 none, 1 SiLU.  fp32.
 void launch_small_linear(const float* in, long long ld_in, const float* W, const float* bias,
                          float* out, long long ld_out, int B, int N, int K, int out_act,
-                         cudaStream_t s);
+                         cudaStream_t s, int groups = 1);
 
 // GroupNorm-apply + SiLU + conv3x3 (C -> Cout small) -> NCHW out (unet.py:145-149)
 void launch_conv_out(const float* h, const double* stats, const float* gamma, const float* beta,

@@ -343,7 +343,8 @@ struct Builder {
   double* gn_pool = nullptr;
   size_t gn_pool_doubles = 0, gn_used = 0;
   const float* emb_all = nullptr;  // [B, emb_total]
-  const float* cross_v = nullptr;  // [B, n_st * d_attn]  (n_cond == 1)
+  const float* cross_cv = nullptr;  // [B, n_st * tf_layers * d_attn] cross-attention output vectors (n_cond == 1)
+  long long cross_cv_ld = 0;
   int st_index = 0;
   const float* cond_ext = nullptr;
 
@@ -444,8 +445,9 @@ struct Builder {
   }
 
   void small_linear(const float* in, long long ld_in, const float* Wt, const float* bias, float* out,
-                    long long ld_out, int N, int K, int out_act, int ext = EXT_NONE) {
+                    long long ld_out, int N, int K, int out_act, int ext = EXT_NONE, int groups = 1) {
     Op& op = push(OP_SMALL_LINEAR);
+    op.i[6] = groups;
     op.ext = ext;
     op.p[0] = in; op.p[1] = Wt; op.p[2] = bias;
     op.o[0] = out;
@@ -506,6 +508,10 @@ struct Builder {
     static const bool one_cta = std::getenv("PF_GEMM_1CTA") != nullptr;
     const bool two = !one_cta && ((B * g.tiles_per_img) % 2 == 0);
     g.two_cta = two ? 1 : 0;
+    // stacked [B_hi ; B_lo] operand (2 MMAs per K step, fewer smem operand reads) for BN <= 128;
+    // PF_GEMM_STACK = 0 (off) / 64 / 128 (only that tile width) for A/B measurements
+    static const int stack_sel = std::getenv("PF_GEMM_STACK") ? std::atoi(std::getenv("PF_GEMM_STACK")) : -1;
+    g.stack = (two && bn <= 128 && (stack_sel < 0 || stack_sel == bn)) ? 1 : 0;
     fill_seg(g.seg[0], a0, w0, two ? bn / 2 : bn, box_w, box_h);
     g.seg[0].b_row0 = row0;
     g.nseg = 1;
@@ -759,17 +765,10 @@ struct Builder {
       }
       float* xattn = nullptr;
       if (n_cond == 1) {
-        // softmax over a single key == 1: attn2(.) == to_out(to_v(cond)) for every token.
-        // cv[b] = Wout2 . v[b] + bout2 + bout1 is added in the attn1 out-projection epilogue.
-        float* cv = alloc<float>(static_cast<size_t>(B) * C);
-        small_linear(cross_v + static_cast<size_t>(sti * c.tf_layers + li) * C,
-                     static_cast<long long>(m->n_st) * c.tf_layers * C,
-                     F(m, tb + ".attn2.to_out.0.weight"),
-                     Fsum(m, tb + ".attn1.to_out.0.bias", tb + ".attn2.to_out.0.bias"), cv, C, C, C, 0);
+        // cross-attention with one key: the per-sample vector computed up front (build())
         Op& op = conv_gemm(so, wo, nullptr, nullptr, H, Wd, C);
-        out_f32(op, x1, C, cv, C, t0, C);
+        out_f32(op, x1, C, cross_cv + static_cast<size_t>(sti * c.tf_layers + li) * C, cross_cv_ld, t0, C);
         free_split(o);
-        arena.free(cv);
         xattn = x1;
       } else {
         Op& op = conv_gemm(so, wo, nullptr, nullptr, H, Wd, C);
@@ -981,11 +980,29 @@ struct Builder {
       for (auto& b : m->output_blocks) collect(b);
       const int d_attn = c.n_heads * 64;
       const float* wv = Fcat(m, "cross_v.weight", vn, nullptr);
+      // to_out of every cross-attention (+ both out-projection biases), one group per transformer
+      std::vector<std::string> on, b1, b2;
+      for (auto& v : vn) {
+        const std::string tb = v.substr(0, v.size() - std::string(".attn2.to_v.weight").size());
+        on.push_back(tb + ".attn2.to_out.0.weight");
+        b1.push_back(tb + ".attn1.to_out.0.bias");
+        b2.push_back(tb + ".attn2.to_out.0.bias");
+      }
+      const float* wo = Fcat(m, "cross_o.weight", on, nullptr);
+      const float* bo = Fcat(m, "cross_o.bias", b1, &b2);
       if (n_cond == 1) {
-        const int nv = static_cast<int>(vn.size()) * d_attn;
+        const int ng = static_cast<int>(vn.size());
+        const int nv = ng * d_attn;
         float* cvall = alloc<float>(static_cast<size_t>(B) * nv);
         small_linear(nullptr, c.d_cond, wv, nullptr, cvall, nv, nv, c.d_cond, 0, EXT_COND);
-        cross_v = cvall;
+        // softmax over a single key == 1: attn2(.) == to_out(to_v(cond)) for every token;
+        // cross_cv[b, g] = Wout2_g . v_g[b] + bout2_g + bout1_g is added in the attn1 out-projection
+        // epilogue of transformer g (all groups in ONE launch)
+        float* cv = alloc<float>(static_cast<size_t>(B) * nv);
+        small_linear(cvall, nv, wo, bo, cv, nv, d_attn, d_attn, 0, EXT_NONE, ng);
+        cross_cv = cv;
+        cross_cv_ld = nv;
+        arena.free(cvall);
       }
     }
     // ---- blocks
@@ -1006,8 +1023,11 @@ struct Builder {
             op.p[1] = F(m, l.name + ".weight"); op.p[2] = F(m, l.name + ".bias");
             op.o[0] = nxt.p;
             op.i[0] = B; op.i[1] = l.cin; op.i[2] = H; op.i[3] = Wd; op.i[4] = l.cout;
-            // its GroupNorm statistics are needed twice (next ResBlock, last skip): reduce once
-            nxt.stats = const_cast<double*>(stats_of(nxt));
+            // its GroupNorm statistics are needed twice (next ResBlock, last skip): reduced once,
+            // inside the conv kernel
+            PF_CHECK(l.cout % 4 == 0 && 256 % (l.cout / 4) == 0 && l.cout <= 256, "first conv: unsupported Cout=%d", l.cout);
+            nxt.stats = new_stats(l.cout);
+            op.o[1] = nxt.stats;
             break;
           }
           case Layer::RES: nxt = res_block(l, cur, first ? skip : nullptr); break;
@@ -1075,8 +1095,8 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
         break;
       case OP_CONV_IN:
         launch_conv_in(x, static_cast<const float*>(op.p[1]), static_cast<const float*>(op.p[2]),
-                       static_cast<float*>(op.o[0]), (int)op.i[0], (int)op.i[1], (int)op.i[2],
-                       (int)op.i[3], (int)op.i[4], s);
+                       static_cast<float*>(op.o[0]), static_cast<double*>(op.o[1]), (int)op.i[0],
+                       (int)op.i[1], (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
         break;
       case OP_GN_STATS:
         launch_gn_stats(static_cast<const float*>(op.p[0]), static_cast<double*>(op.o[0]), (int)op.i[0],
@@ -1111,7 +1131,7 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
         launch_small_linear(op.ext == EXT_COND ? cond : static_cast<const float*>(op.p[0]), op.i[0],
                             static_cast<const float*>(op.p[1]), static_cast<const float*>(op.p[2]),
                             static_cast<float*>(op.o[0]), op.i[1], (int)op.i[2], (int)op.i[3],
-                            (int)op.i[4], (int)op.i[5], s);
+                            (int)op.i[4], (int)op.i[5], s, op.i[6] > 0 ? (int)op.i[6] : 1);
         break;
       case OP_CONV_OUT:
         launch_conv_out(static_cast<const float*>(op.p[0]), static_cast<const double*>(op.p[1]),
@@ -1329,9 +1349,10 @@ int pf_unet_op_desc(pf_unet* h, int32_t i, char* buf, int32_t len) {
       const GemmParams& g = op.g;
       int k = 0;
       for (int s = 0; s < g.nseg; ++s) k += g.seg[s].ntaps * g.seg[s].kb_per_tap * 64;
-      snprintf(buf, len, "gemm M=%lld N=%d K=%d bn=%d taps=%d nseg=%d z=%d mode=%d stages=%d cta%d",
+      snprintf(buf, len, "gemm M=%lld N=%d K=%d bn=%d taps=%d nseg=%d z=%d mode=%d stages=%d cta%d%s",
                static_cast<long long>(g.m_tiles) * 128, g.n_tiles * op.bn, k, op.bn, g.seg[0].ntaps,
-               g.nseg, g.z_count, g.mode, g.nstages, g.two_cta ? 2 : 1);
+               g.nseg, g.z_count, g.mode, g.nstages, g.two_cta ? 2 : 1,
+               (g.two_cta && g.stack && op.bn <= 128) ? "s" : "");
     } else if (op.kind == OP_ACT_SPLIT) {
       snprintf(buf, len, "act_split C=%d+%d HxW=%dx%d B=%d norm=%d silu=%d layout=%d dual=%d", op.as.C0,
                op.as.C1, op.as.H, op.as.W, op.as.B, op.as.stats0 != nullptr, op.as.silu, op.as.layout,
