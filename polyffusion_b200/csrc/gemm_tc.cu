@@ -56,9 +56,19 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, long long 
 // The accumulator of a tile is then 2 BN columns wide,
 //   [0, h) hi*hi (n < h) | [h, BN) hi*lo + lo*hi (n < h) | [BN, BN+h) hi*hi + lo*hi (n >= h) | [BN+h, 2BN) hi*lo (n >= h)
 // with h = BN / 2, and the epilogue adds the two pieces of every output column.
-template <int BN, bool TWO, int MODE, bool STATS, bool STACK>
+//
+// HALO (cta_group::2, tiles that are one image row of 128 pixels): the three dx taps of a 3x3
+// convolution row are served from ONE 130-pixel halo row in shared memory.  The UMMA descriptor of
+// tap dx simply starts dx rows (128 B each) further in: SWIZZLE_128B is applied to absolute
+// shared-memory address bits, so a start address that is not a multiple of the 1024-byte atom reads
+// the rows TMA wrote there (verified on B200 with tools/probe_umma_shift.cu; the descriptor's base
+// offset field stays 0).  A stage then holds one (dy, k-block): A 2 x 130 rows + the B tiles of three
+// taps, and the A bytes pulled through L2 drop 2.95x.  These N = 64 convolutions at 128 x 128 were
+// bound by L2 -> SM bandwidth (~11 TB/s at 40 KB per 3.1 MFLOP issued), not by the tensor pipe.
+template <int BN, bool TWO, int MODE, bool STATS, bool STACK, bool HALO>
 __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   static_assert(!STACK || (TWO && BN <= 128), "stacked B operand needs cta_group::2 and 4*BN <= 512 TMEM columns");
+  static_assert(!HALO || TWO, "halo stages are implemented for cta_group::2 only");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -68,7 +78,9 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
 
   constexpr int A_BYTES = GEMM_BM * 128;
   constexpr int B_BYTES = (TWO ? BN / 2 : BN) * 128;  // B rows staged by this CTA
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int A_SLOT = HALO ? GEMM_HALO_A_SLOT : A_BYTES;  // bytes reserved per A half (hi / lo)
+  constexpr int GT = HALO ? 3 : 1;                            // taps per stage (B tile pairs reserved)
+  constexpr int STAGE_BYTES = 2 * A_SLOT + GT * 2 * B_BYTES;
   constexpr uint32_t IDESC = TWO ? umma_idesc_bf16_m256(BN) : umma_idesc_bf16(BN);
   constexpr uint32_t IDESC_2N = umma_idesc_bf16_m256(STACK ? 2 * BN : BN);
   constexpr int ACC_COLS = STACK ? 2 * BN : BN;  // TMEM columns of one accumulator stage
@@ -86,8 +98,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   const long long total_tiles =
       static_cast<long long>(p.n_tiles) * (TWO ? p.m_tiles / 2 : p.m_tiles) * p.z_count;
 
-  int nkb = 0;
-  for (int s = 0; s < p.nseg; ++s) nkb += p.seg[s].ntaps * p.seg[s].kb_per_tap;
+  // a stage = one (tap group, k-block); without HALO every group is a single tap
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < nstages; ++i) {
@@ -137,7 +148,12 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           const int brow = sg.b_row0 + tc.zb * sg.b_row_zb + tc.zh * sg.b_row_zh + tc.n0 +
                            (TWO ? static_cast<int>(rank) * (BN / 2) : 0);
           const int bcol = sg.b_col0 + tc.zb * sg.b_col_zb + tc.zh * sg.b_col_zh;
-          for (int tp = 0; tp < sg.ntaps; ++tp) {
+          const int gtaps = HALO ? sg.gtaps : 1;
+          const int ngroups = HALO ? sg.ngroups : sg.ntaps;
+          const uint32_t tx = 2u * static_cast<uint32_t>(HALO ? sg.a_rows * 128 : A_BYTES) +
+                              static_cast<uint32_t>(gtaps) * 2u * B_BYTES;  // bytes per CTA per stage
+          for (int g = 0; g < ngroups; ++g) {
+            const int tp = g * gtaps;
             const int ax = tc.x0 + sg.tap_dx[tp], ay = tc.y0 + sg.tap_dy[tp];
             const int ai = aimg + sg.tap_dq[tp];
             const int br = brow + tp * sg.b_tap_stride;
@@ -149,13 +165,19 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
               const uint32_t sa = ring + stage * STAGE_BYTES;
               if (TWO) {
                 // both CTAs' loads complete on the LEADER's barrier, which expects both halves
-                if (leader) mbar_expect_tx(fb, 2 * STAGE_BYTES);
+                if (leader) mbar_expect_tx(fb, 2 * tx);
                 tma2_load_4d(sa, &sg.a_hi, fb, acol + kb * GEMM_BK, ax, ay, ai);
-                tma2_load_4d(sa + A_BYTES, &sg.a_lo, fb, acol + kb * GEMM_BK, ax, ay, ai);
-                tma2_load_2d(sa + 2 * A_BYTES, &sg.b_hi, fb, bcol + kb * GEMM_BK, br);
-                tma2_load_2d(sa + 2 * A_BYTES + B_BYTES, &sg.b_lo, fb, bcol + kb * GEMM_BK, br);
+                tma2_load_4d(sa + A_SLOT, &sg.a_lo, fb, acol + kb * GEMM_BK, ax, ay, ai);
+#pragma unroll
+                for (int j = 0; j < GT; ++j) {
+                  if (j < gtaps) {
+                    const uint32_t sb = sa + 2 * A_SLOT + j * 2 * B_BYTES;
+                    tma2_load_2d(sb, &sg.b_hi, fb, bcol + kb * GEMM_BK, br + j * sg.b_tap_stride);
+                    tma2_load_2d(sb + B_BYTES, &sg.b_lo, fb, bcol + kb * GEMM_BK, br + j * sg.b_tap_stride);
+                  }
+                }
               } else {
-                mbar_expect_tx(fb, STAGE_BYTES);
+                mbar_expect_tx(fb, tx);
                 tma_load_4d(sa, &sg.a_hi, fb, acol + kb * GEMM_BK, ax, ay, ai);
                 tma_load_4d(sa + A_BYTES, &sg.a_lo, fb, acol + kb * GEMM_BK, ax, ay, ai);
                 tma_load_2d(sa + 2 * A_BYTES, &sg.b_hi, fb, bcol + kb * GEMM_BK, br);
@@ -177,34 +199,47 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1u);
         tc_fence_after();
         const uint32_t acc = tmem_base + static_cast<uint32_t>(as * ACC_COLS);
-        for (int kbi = 0; kbi < nkb; ++kbi, ++it) {
-          const int stage = it % nstages;
-          const uint32_t ph = static_cast<uint32_t>(it / nstages) & 1u;
-          mbar_wait(smem_u32(&full_bar[stage]), ph);
-          tc_fence_after();
-          const uint32_t sa = ring + stage * STAGE_BYTES;
-          const uint64_t da_hi = umma_desc_sw128(sa);
-          const uint64_t da_lo = umma_desc_sw128(sa + A_BYTES);
-          const uint64_t db_hi = umma_desc_sw128(sa + 2 * A_BYTES);
-          const uint64_t db_lo = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+        int kbi = 0;  // stages consumed for this tile
+        for (int s = 0; s < p.nseg; ++s) {
+          const GemmSeg& sg = p.seg[s];
+          const int gtaps = HALO ? sg.gtaps : 1;
+          const int nst = (HALO ? sg.ngroups : sg.ntaps) * sg.kb_per_tap;
+          for (int si = 0; si < nst; ++si, ++kbi, ++it) {
+            const int stage = it % nstages;
+            const uint32_t ph = static_cast<uint32_t>(it / nstages) & 1u;
+            mbar_wait(smem_u32(&full_bar[stage]), ph);
+            tc_fence_after();
+            const uint32_t sa = ring + stage * STAGE_BYTES;
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t ko = static_cast<uint64_t>(k * 2);  // 32 B per K=16 step (16 B units)
-            if (STACK) {
-              umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC_2N, (kbi | k) != 0);
-              umma2_bf16(acc + BN / 2, da_lo + ko, db_hi + ko, IDESC, 1u);
-            } else if (TWO) {
-              umma2_bf16(acc, da_lo + ko, db_hi + ko, IDESC, (kbi | k) != 0);
-              umma2_bf16(acc, da_hi + ko, db_lo + ko, IDESC, 1u);
-              umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC, 1u);
-            } else {
-              umma_bf16(acc, da_lo + ko, db_hi + ko, IDESC, (kbi | k) != 0);
-              umma_bf16(acc, da_hi + ko, db_lo + ko, IDESC, 1u);
-              umma_bf16(acc, da_hi + ko, db_hi + ko, IDESC, 1u);
+            for (int j = 0; j < GT; ++j) {
+              if (j < gtaps) {
+                // tap j of the group: A starts j halo rows (128 B each) further in
+                const uint64_t da_hi = umma_desc_sw128(sa + j * 128);
+                const uint64_t da_lo = umma_desc_sw128(sa + A_SLOT + j * 128);
+                const uint64_t db_hi = umma_desc_sw128(sa + 2 * A_SLOT + j * 2 * B_BYTES);
+                const uint64_t db_lo = umma_desc_sw128(sa + 2 * A_SLOT + j * 2 * B_BYTES + B_BYTES);
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k) {
+                  const uint64_t ko = static_cast<uint64_t>(k * 2);  // 32 B per K=16 step (16 B units)
+                  const uint32_t accum = (kbi | j | k) != 0;
+                  if (STACK) {
+                    umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC_2N, accum);
+                    umma2_bf16(acc + BN / 2, da_lo + ko, db_hi + ko, IDESC, 1u);
+                  } else if (TWO) {
+                    umma2_bf16(acc, da_lo + ko, db_hi + ko, IDESC, accum);
+                    umma2_bf16(acc, da_hi + ko, db_lo + ko, IDESC, 1u);
+                    umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC, 1u);
+                  } else {
+                    umma_bf16(acc, da_lo + ko, db_hi + ko, IDESC, accum);
+                    umma_bf16(acc, da_hi + ko, db_lo + ko, IDESC, 1u);
+                    umma_bf16(acc, da_hi + ko, db_hi + ko, IDESC, 1u);
+                  }
+                }
+              }
             }
+            if (TWO) umma2_commit_mc(smem_u32(&empty_bar[stage]));
+            else umma_commit(smem_u32(&empty_bar[stage]));
           }
-          if (TWO) umma2_commit_mc(smem_u32(&empty_bar[stage]));
-          else umma_commit(smem_u32(&empty_bar[stage]));
         }
         if (TWO) umma2_commit_mc(smem_u32(&tmem_full_bar[as]));
         else umma_commit(smem_u32(&tmem_full_bar[as]));
@@ -452,20 +487,27 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
 
 template <int BN, int MODE, bool STATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  gemm_body<BN, false, MODE, STATS, false>(p);
+  gemm_body<BN, false, MODE, STATS, false, false>(p);
 }
 
 template <int BN, int MODE, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
-  gemm_body<BN, true, MODE, STATS, false>(p);
+  gemm_body<BN, true, MODE, STATS, false, false>(p);
 }
 
 // cta_group::2 with the stacked [B_hi ; B_lo] operand (BN <= 128)
 template <int BN, int MODE, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc2s_kernel(const __grid_constant__ GemmParams p) {
-  gemm_body<BN, true, MODE, STATS, true>(p);
+  gemm_body<BN, true, MODE, STATS, true, false>(p);
+}
+
+// stacked B + halo stages (one 130-pixel A row serves the three dx taps); fp32 output only
+template <int BN, bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc2h_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, true, OUT_F32, STATS, true, true>(p);
 }
 
 typedef void (*GemmKernel)(GemmParams);
@@ -502,6 +544,10 @@ static GemmKernel pick_variant(int v) {
 }
 
 static GemmKernel pick_kernel(int bn, int kind, int v) {
+  if (kind == 3) {  // halo stages: BN = 64, fp32 output (with / without statistics)
+    if (bn != 64 || v > 1) return nullptr;
+    return v == 1 ? gemm_tc2h_kernel<64, true> : gemm_tc2h_kernel<64, false>;
+  }
   switch (bn) {
     case 64: return kind == 2 ? pick_variant<64, 2>(v) : kind == 1 ? pick_variant<64, 1>(v) : pick_variant<64, 0>(v);
     case 128: return kind == 2 ? pick_variant<128, 2>(v) : kind == 1 ? pick_variant<128, 1>(v) : pick_variant<128, 0>(v);
@@ -512,7 +558,7 @@ static GemmKernel pick_kernel(int bn, int kind, int v) {
 
 cudaError_t gemm_init_attrs() {
   for (int bn : {64, 128, 256})
-    for (int kind = 0; kind < 3; ++kind)
+    for (int kind = 0; kind < 4; ++kind)
       for (int v = 0; v < 5; ++v) {
         GemmKernel k = pick_kernel(bn, kind, v);
         if (!k) continue;
@@ -531,11 +577,12 @@ cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t 
     case OUT_SPLIT_T: v = 3; break;
     default: v = 4; break;
   }
-  const int kind = p.two_cta ? ((p.stack && bn <= 128) ? 2 : 1) : 0;
+  const int kind = p.two_cta ? (p.halo ? 3 : (p.stack && bn <= 128) ? 2 : 1) : 0;
   GemmKernel k = pick_kernel(bn, kind, v);
   if (!k) return cudaErrorInvalidValue;
   if (p.two_cta) {
-    const int smem = p.nstages * gemm_stage_bytes2(bn) + 1024 + gemm_epilogue_smem_bytes(bn);
+    const int smem = p.nstages * (p.halo ? gemm_stage_bytes2_halo(bn) : gemm_stage_bytes2(bn)) + 1024 +
+                     gemm_epilogue_smem_bytes(bn);
     const long long pairs = static_cast<long long>(p.n_tiles) * (p.m_tiles / 2) * p.z_count;
     const long long max_clusters = num_ctas / 2;
     const unsigned grid = 2u * static_cast<unsigned>(pairs < max_clusters ? pairs : max_clusters);

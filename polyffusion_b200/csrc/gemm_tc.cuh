@@ -21,6 +21,8 @@ constexpr int GEMM_BM = 128;      // output rows (pixels / tokens) per CTA
 constexpr int GEMM_BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 320; // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int GEMM_MAX_TAPS = 12;
+constexpr int GEMM_HALO_ROWS = 130;            // halo stage: one image row of 128 pixels + 1 on each side
+constexpr int GEMM_HALO_A_SLOT = 17 * 1024;    // 130 x 128 B rounded up to the 1024-byte swizzle atom
 
 enum GemmOutMode : int {
   OUT_F32 = 0,        // fp32 row-major [m, ldc] (+ addvec[img, n] + resid[m, n])
@@ -39,7 +41,9 @@ struct alignas(64) GemmSeg {
   int a_img_zb, a_img_zh, a_col_zb, a_col_zh;  // per-batch (z) coordinate offsets
   int b_row_zb, b_row_zh, b_col_zb, b_col_zh;
   signed char tap_dx[GEMM_MAX_TAPS], tap_dy[GEMM_MAX_TAPS], tap_dq[GEMM_MAX_TAPS];
-  int pad1[3];
+  // halo kernels only: taps [g*gtaps, (g+1)*gtaps) share one A box of a_rows pixels (tap j starts j
+  // rows in); other kernels ignore these (every tap is its own stage)
+  int ngroups, gtaps, a_rows;
 };
 
 struct alignas(64) GemmParams {
@@ -64,6 +68,7 @@ struct alignas(64) GemmParams {
   int geglu_f;          // OUT_GEGLU: number of output features F (bias layout [x: F | gate: F])
   int two_cta;          // 1: cta_group::2 kernel (tile pairs; B maps have boxes of BN/2 rows)
   int stack;            // 1 (with two_cta, BN <= 128): stacked [B_hi ; B_lo] operand, 2 MMAs per K step
+  int halo;             // 1 (with two_cta, BN = 64, box 128 x 1, OUT_F32): halo stages, see gemm_tc.cu
   // nearest-2x-upsample + conv3x3 evaluated as four 2x2 parity convolutions at LOW resolution:
   // OUT_F32 rows are scattered to pixel (2y + up_py, 2x + up_px) of the [img][2H][2W] output
   int up_mode, up_py, up_px;
@@ -75,6 +80,8 @@ inline int gemm_stage_bytes(int bn) { return 2 * GEMM_BM * 128 + 2 * bn * 128; }
 inline int gemm_smem_bytes(int bn, int nstages) { return nstages * gemm_stage_bytes(bn) + 1024; }
 // cta_group::2: each CTA stages its 128 A rows and half of the B rows
 inline int gemm_stage_bytes2(int bn) { return 2 * GEMM_BM * 128 + bn * 128; }
+// halo stages: 2 A slots of 130 rows + the half-B tile pairs of three taps
+inline int gemm_stage_bytes2_halo(int bn) { return 2 * GEMM_HALO_A_SLOT + 3 * bn * 128; }
 // epilogue staging: 8 warps x (32 rows x 32 fp32)
 inline int gemm_epilogue_smem_bytes(int /*bn*/) { return 8 * 32 * 32 * 4; }
 

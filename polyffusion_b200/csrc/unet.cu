@@ -462,7 +462,8 @@ struct Builder {
     int kind;     // 0 = 1x1 (no shift), 1 = 3x3, 2 = 3x3 stride-2 over S2D planes
   };
 
-  void fill_seg(GemmSeg& sg, const ASrc& a, PackedW& w, int b_box_rows, int box_w, int box_h) {
+  void fill_seg(GemmSeg& sg, const ASrc& a, PackedW& w, int b_box_rows, int box_w, int box_h,
+                bool halo = false) {
     memset(&sg, 0, sizeof sg);
     if (a.kind == 0) fill_taps_1x1(sg);
     else if (a.kind == 1) fill_taps_3x3(sg);
@@ -481,6 +482,12 @@ struct Builder {
     PF_CHECK(a.C == w.K, "GEMM K mismatch: operand has %d channels, weight expects %d", a.C, w.K);
     sg.kb_per_tap = a.C / 64;
     sg.b_tap_stride = w.rows;
+    // halo stages (gemm_tc.cu): the three dx taps of a 3x3 row share one 130-pixel A box
+    const bool grouped = halo && a.kind == 1;
+    sg.ngroups = grouped ? 3 : sg.ntaps;
+    sg.gtaps = grouped ? 3 : 1;
+    sg.a_rows = grouped ? GEMM_HALO_ROWS : 128;
+    if (grouped) box_w = GEMM_HALO_ROWS;
     if (!dry) {
       sg.a_hi = make_map_4d(a.buf.hi, a.C, a.W, a.H, a.N, box_w, box_h);
       sg.a_lo = make_map_4d(a.buf.lo, a.C, a.W, a.H, a.N, box_w, box_h);
@@ -512,14 +519,21 @@ struct Builder {
     // PF_GEMM_STACK = 0 (off) / 64 / 128 (only that tile width) for A/B measurements
     static const int stack_sel = std::getenv("PF_GEMM_STACK") ? std::atoi(std::getenv("PF_GEMM_STACK")) : -1;
     g.stack = (two && bn <= 128 && (stack_sel < 0 || stack_sel == bn)) ? 1 : 0;
-    fill_seg(g.seg[0], a0, w0, two ? bn / 2 : bn, box_w, box_h);
+    // halo stages for the N = 64 3x3 convolutions at 128 x 128 (tile = one image row): A bytes
+    // through L2 drop 2.95x (these launches were L2 -> SM bandwidth bound).  PF_GEMM_HALO=0 disables.
+    static const bool halo_ok = !(std::getenv("PF_GEMM_HALO") && std::atoi(std::getenv("PF_GEMM_HALO")) == 0);
+    const bool halo = halo_ok && two && g.stack && bn == 64 && box_w == 128 && box_h == 1 && a0.kind == 1 &&
+                      (!a1 || a1->kind == 0);
+    g.halo = halo ? 1 : 0;
+    fill_seg(g.seg[0], a0, w0, two ? bn / 2 : bn, box_w, box_h, halo);
     g.seg[0].b_row0 = row0;
     g.nseg = 1;
     if (a1) {
-      fill_seg(g.seg[1], *a1, *w1, two ? bn / 2 : bn, box_w, box_h);
+      fill_seg(g.seg[1], *a1, *w1, two ? bn / 2 : bn, box_w, box_h, halo);
       g.nseg = 2;
     }
     g.nstages = two ? gemm_default_stages2(bn) : gemm_default_stages(bn);
+    if (halo) g.nstages = std::min(6, (226 * 1024 - 1024 - 32768) / gemm_stage_bytes2_halo(bn));
     g.box_w = box_w;
     g.box_h = box_h;
     g.zdiv = 1;
@@ -1352,7 +1366,7 @@ int pf_unet_op_desc(pf_unet* h, int32_t i, char* buf, int32_t len) {
       snprintf(buf, len, "gemm M=%lld N=%d K=%d bn=%d taps=%d nseg=%d z=%d mode=%d stages=%d cta%d%s",
                static_cast<long long>(g.m_tiles) * 128, g.n_tiles * op.bn, k, op.bn, g.seg[0].ntaps,
                g.nseg, g.z_count, g.mode, g.nstages, g.two_cta ? 2 : 1,
-               (g.two_cta && g.stack && op.bn <= 128) ? "s" : "");
+               g.halo ? "sh" : (g.two_cta && g.stack && op.bn <= 128) ? "s" : "");
     } else if (op.kind == OP_ACT_SPLIT) {
       snprintf(buf, len, "act_split C=%d+%d HxW=%dx%d B=%d norm=%d silu=%d layout=%d dual=%d", op.as.C0,
                op.as.C1, op.as.H, op.as.W, op.as.B, op.as.stats0 != nullptr, op.as.silu, op.as.layout,
