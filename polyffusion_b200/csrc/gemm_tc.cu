@@ -269,7 +269,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
       const long long m0 = static_cast<long long>(tc.tile) * GEMM_BM + q * 32;  // first row of this warp
       const long long zoff = tc.zb * p.out_zb + tc.zh * p.out_zh;
-      if (MODE == OUT_F32 && p.resid != nullptr) {
+      if ((MODE == OUT_F32 || MODE == OUT_SPLIT) && p.resid != nullptr) {
         // Pull this warp's share of the residual into L2 one tile AHEAD (the residual was written
         // several kernels ago and has usually left L2; a DRAM round trip per chunk would otherwise
         // dominate the epilogue of the small-K GEMMs): one 128-byte line per (row, 32-col chunk).
@@ -335,7 +335,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         const int ncols = geglu ? BN / 2 : BN;          // output columns produced by this tile
         const int ocol0 = geglu ? (tc.n0 / 2) : tc.n0;  // first output column
         const float* av = p.addvec ? p.addvec + static_cast<long long>(tc.img) * p.addvec_ld : nullptr;
-        const bool has_res = (MODE == OUT_F32) && p.resid != nullptr;
+        const bool has_res = (MODE == OUT_F32 || MODE == OUT_SPLIT) && p.resid != nullptr;
         float4 csum[STATS ? BN / 64 : 1], csq[STATS ? BN / 64 : 1];  // per-chunk column partial sums
 #pragma unroll(STATS ? BN / 64 : 1)
         for (int ci = 0; ci < BN / 64; ++ci) {
@@ -411,7 +411,12 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y);
                 ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
               }
-            } else {  // OUT_SPLIT / OUT_GEGLU: split-bf16 row-major
+            } else {  // OUT_SPLIT (+ residual) / OUT_GEGLU: split-bf16 row-major
+              if constexpr (MODE == OUT_SPLIT) {
+                if (has_res) {
+                  o.x += rres[it].x; o.y += rres[it].y; o.z += rres[it].z; o.w += rres[it].w;
+                }
+              }
               uint2 h, l;
               split2(o.x, o.y, h.x, l.x);
               split2(o.z, o.w, h.y, l.y);

@@ -26,7 +26,7 @@ constexpr int GEMM_HALO_A_SLOT = 17 * 1024;    // 130 x 128 B rounded up to the 
 
 enum GemmOutMode : int {
   OUT_F32 = 0,        // fp32 row-major [m, ldc] (+ addvec[img, n] + resid[m, n])
-  OUT_SPLIT = 1,      // bf16 hi/lo row-major [m, ldc]
+  OUT_SPLIT = 1,      // bf16 hi/lo row-major [m, ldc] of (acc + addvec[img, n] + resid[m, n])
   OUT_SPLIT_T = 2,    // bf16 hi/lo transposed per image: [img][n][token]
   OUT_GEGLU = 3,      // tile = [BN/2 value cols | BN/2 gate cols]: split-bf16 of (x+b)*gelu(g+b)
 };

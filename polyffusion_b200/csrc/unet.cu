@@ -332,6 +332,9 @@ struct T {  // fp32 NHWC activation
   float* p = nullptr;
   int C = 0, H = 0, W = 0;
   double* stats = nullptr;  // per-(sample, channel) sum / sum-of-squares [B][C][2], if produced
+  // set instead of p when the only consumer wants the plain split-bf16 operand (UpSample input):
+  // the producing GEMM's epilogue wrote it directly, no fp32 copy exists
+  Split sp;
 };
 
 struct Builder {
@@ -499,8 +502,9 @@ struct Builder {
 
   // conv / linear GEMM over B images of Ho x Wo output pixels.
   // seg1 (optional) is a 1x1 segment accumulated into the same tile (ResBlock skip conv).
+  // f32_out = false: the caller will select a split output mode (no halo kernel for those)
   Op& conv_gemm(const ASrc& a0, PackedW& w0, const ASrc* a1, PackedW* w1, int Ho, int Wo, int Cout,
-                int row0 = 0, int bn_override = 0) {
+                int row0 = 0, int bn_override = 0, bool f32_out = true) {
     const int bn = bn_override ? bn_override : choose_bn(Cout);
     const int box_w = choose_box_w(Wo);
     PF_CHECK(128 % box_w == 0 && Wo % box_w == 0, "unsupported width %d", Wo);
@@ -522,7 +526,7 @@ struct Builder {
     // halo stages for the N = 64 3x3 convolutions at 128 x 128 (tile = one image row): A bytes
     // through L2 drop 2.95x (these launches were L2 -> SM bandwidth bound).  PF_GEMM_HALO=0 disables.
     static const bool halo_ok = !(std::getenv("PF_GEMM_HALO") && std::atoi(std::getenv("PF_GEMM_HALO")) == 0);
-    const bool halo = halo_ok && two && g.stack && bn == 64 && box_w == 128 && box_h == 1 && a0.kind == 1 &&
+    const bool halo = halo_ok && f32_out && two && g.stack && bn == 64 && box_w == 128 && box_h == 1 && a0.kind == 1 &&
                       (!a1 || a1->kind == 0);
     g.halo = halo ? 1 : 0;
     fill_seg(g.seg[0], a0, w0, two ? bn / 2 : bn, box_w, box_h, halo);
@@ -556,8 +560,22 @@ struct Builder {
     op.g.ldr = ldr;
   }
 
+  // split-bf16 output of (acc + addvec + resid): the consumer is a GEMM that takes the value as is
+  void out_split(Op& op, const Split& out, int ldc, const float* addvec, long long addvec_ld,
+                 const float* resid, long long ldr) {
+    op.g.mode = OUT_SPLIT;
+    op.g.out_hi = out.hi;
+    op.g.out_lo = out.lo;
+    op.g.ldc = ldc;
+    op.g.addvec = addvec;
+    op.g.addvec_ld = addvec_ld;
+    op.g.resid = resid;
+    op.g.ldr = ldr;
+  }
+
   // ---------------------------------------------------------------- layers
-  T res_block(const Layer& L, const T& x0, const T* x1) {
+  // split_only: the output feeds nothing but an UpSample conv -> emit its plain split operand
+  T res_block(const Layer& L, const T& x0, const T* x1, bool split_only = false) {
     const int C = x0.C + (x1 ? x1->C : 0);
     PF_CHECK(C == L.cin, "ResBlock %s: got %d input channels, expected %d", L.name.c_str(), C, L.cin);
     const int H = x0.H, Wd = x0.W;
@@ -581,21 +599,27 @@ struct Builder {
     arena.free(h1.p);
     T y;
     y.C = L.cout; y.H = H; y.W = Wd;
-    y.p = alloc<float>(npix * L.cout);
-    y.stats = new_stats(L.cout);
+    if (split_only) y.sp = alloc_split(npix * L.cout);
+    else {
+      y.p = alloc<float>(npix * L.cout);
+      y.stats = new_stats(L.cout);
+    }
     PackedW& w2 = W(m, L.name + ".out_layers.3.weight", {L.name + ".out_layers.3.weight"});
     ASrc s2{a2, L.cout, Wd, H, B, 1};
     if (L.cin != L.cout) {
       PackedW& ws = W(m, L.name + ".skip_connection.weight", {L.name + ".skip_connection.weight"});
       ASrc s3{a3, C, Wd, H, B, 0};
-      Op& op = conv_gemm(s2, w2, &s3, &ws, H, Wd, L.cout);
-      out_f32(op, y.p, L.cout, Fsum(m, L.name + ".out_layers.3.bias", L.name + ".skip_connection.bias"),
-              0, nullptr, 0, y.stats);
+      const float* bsum = Fsum(m, L.name + ".out_layers.3.bias", L.name + ".skip_connection.bias");
+      Op& op = conv_gemm(s2, w2, &s3, &ws, H, Wd, L.cout, 0, 0, !split_only);
+      if (split_only) out_split(op, y.sp, L.cout, bsum, 0, nullptr, 0);
+      else out_f32(op, y.p, L.cout, bsum, 0, nullptr, 0, y.stats);
       free_split(a3);
     } else {
       PF_CHECK(!x1, "identity skip with concatenated input");
-      Op& op = conv_gemm(s2, w2, nullptr, nullptr, H, Wd, L.cout);
-      out_f32(op, y.p, L.cout, F(m, L.name + ".out_layers.3.bias"), 0, x0.p, x0.C, y.stats);
+      Op& op = conv_gemm(s2, w2, nullptr, nullptr, H, Wd, L.cout, 0, 0, !split_only);
+      const float* b2 = F(m, L.name + ".out_layers.3.bias");
+      if (split_only) out_split(op, y.sp, L.cout, b2, 0, x0.p, x0.C);
+      else out_f32(op, y.p, L.cout, b2, 0, x0.p, x0.C, y.stats);
     }
     free_split(a2);
     return y;
@@ -715,7 +739,7 @@ struct Builder {
     free_split(P);
   }
 
-  T spatial_transformer(const Layer& L, const T& x) {
+  T spatial_transformer(const Layer& L, const T& x, bool split_only = false) {
     const pf_unet_cfg& c = m->cfg;
     const int C = x.C, H = x.H, Wd = x.W, N = H * Wd;
     const int heads = c.n_heads;
@@ -734,6 +758,8 @@ struct Builder {
     }
     free_split(a);
 
+    PF_CHECK(c.tf_layers >= 1, "SpatialTransformer without transformer blocks");
+    Split ao;  // operand of proj_out
     for (int li = 0; li < c.tf_layers; ++li) {
       const std::string tb = L.name + ".transformer_blocks." + std::to_string(li);
       // ---- self attention: x = attn1(norm1(x)) + x
@@ -854,31 +880,40 @@ struct Builder {
         op.g.geglu_f = Fh;
       }
       free_split(l3);
-      float* x3 = alloc<float>(rows * C);
+      const bool last = (li + 1 == c.tf_layers);
+      float* x3 = nullptr;
       {
         ASrc s{e, Fh, Wd, H, B, 0};
         Op& op = conv_gemm(s, W(m, tb + ".ff.net.2.weight", {tb + ".ff.net.2.weight"}), nullptr,
-                           nullptr, H, Wd, C);
-        out_f32(op, x3, C, F(m, tb + ".ff.net.2.bias"), 0, xattn, C);
+                           nullptr, H, Wd, C, 0, 0, !last);
+        if (last) {
+          // the last block's output feeds only proj_out: emit its split operand from the epilogue
+          ao = alloc_split(rows * C);
+          out_split(op, ao, C, F(m, tb + ".ff.net.2.bias"), 0, xattn, C);
+        } else {
+          x3 = alloc<float>(rows * C);
+          out_f32(op, x3, C, F(m, tb + ".ff.net.2.bias"), 0, xattn, C);
+        }
       }
       free_split(e);
       arena.free(xattn);
       t0 = x3;
     }
     // proj_out + residual
-    T tt;
-    tt.p = t0; tt.C = C; tt.H = H; tt.W = Wd;
-    Split ao = act_split(tt, nullptr, "", 0.f, false, XF_SAME);
-    arena.free(t0);
     T y;
     y.C = C; y.H = H; y.W = Wd;
-    y.p = alloc<float>(rows * C);
     {
       ASrc s{ao, C, Wd, H, B, 0};
       Op& op = conv_gemm(s, W(m, L.name + ".proj_out.weight", {L.name + ".proj_out.weight"}), nullptr,
-                         nullptr, H, Wd, C);
-      y.stats = new_stats(C);
-      out_f32(op, y.p, C, F(m, L.name + ".proj_out.bias"), 0, x.p, C, y.stats);
+                         nullptr, H, Wd, C, 0, 0, !split_only);
+      if (split_only) {
+        y.sp = alloc_split(rows * C);
+        out_split(op, y.sp, C, F(m, L.name + ".proj_out.bias"), 0, x.p, C);
+      } else {
+        y.p = alloc<float>(rows * C);
+        y.stats = new_stats(C);
+        out_f32(op, y.p, C, F(m, L.name + ".proj_out.bias"), 0, x.p, C, y.stats);
+      }
     }
     free_split(ao);
     return y;
@@ -902,7 +937,7 @@ struct Builder {
   T up_sample(const Layer& L, const T& x) {
     // conv3x3(nearest2x(x)) == four 2x2 convolutions of x, one per output parity (weights folded at
     // finalize): 16 tap-GEMMs at low resolution instead of 36, and no 4x upsampled tensor.
-    Split a = act_split(x, nullptr, "", 0.f, false, XF_SAME);
+    Split a = x.sp.hi ? x.sp : act_split(x, nullptr, "", 0.f, false, XF_SAME);
     T y;
     y.C = x.C; y.H = x.H * 2; y.W = x.W * 2;
     y.p = alloc<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
@@ -1022,10 +1057,14 @@ struct Builder {
     // ---- blocks
     std::vector<T> skips;
     T x;
+    static const bool split_up_ok = std::getenv("PF_NO_SPLIT_UP") == nullptr;
     auto run_block = [&](const BlockSpec& b, T xin, const T* skip) -> T {
       T cur = xin;
       bool first = true;
-      for (auto& l : b.layers) {
+      for (size_t li = 0; li < b.layers.size(); ++li) {
+        const Layer& l = b.layers[li];
+        // an activation consumed only by the block's UpSample conv is produced as its split operand
+        const bool to_up = split_up_ok && li + 1 < b.layers.size() && b.layers[li + 1].kind == Layer::UP;
         T nxt;
         switch (l.kind) {
           case Layer::CONV_IN: {
@@ -1044,8 +1083,8 @@ struct Builder {
             op.o[1] = nxt.stats;
             break;
           }
-          case Layer::RES: nxt = res_block(l, cur, first ? skip : nullptr); break;
-          case Layer::ST: nxt = spatial_transformer(l, cur); break;
+          case Layer::RES: nxt = res_block(l, cur, first ? skip : nullptr, to_up); break;
+          case Layer::ST: nxt = spatial_transformer(l, cur, to_up); break;
           case Layer::DOWN: nxt = down_sample(l, cur); break;
           case Layer::UP: nxt = up_sample(l, cur); break;
         }
