@@ -57,6 +57,18 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def load_gemm_traffic():
+    """DRAM bytes moved by the tcgen05 GEMM launches of ONE step, from the newest committed ncu launch
+    list (profiles/*_gemm_traffic.json, written by tools/ncu_launches_step.py); None if absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    return d["gemm_dram_bytes_read"] + d["gemm_dram_bytes_write"], os.path.relpath(files[-1], ROOT)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
 
@@ -294,6 +306,7 @@ def run_gpu_arm(args):
 
     if rank == 0:
         peaks = load_peaks()
+        traffic, traffic_src = load_gemm_traffic()
         achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         cpu_value, cpu_sec, cores = cpu_port_samples_per_sec(4, 3, 1) if world == 1 and not args.no_cpu else (None, None, None)
         line = {
@@ -322,7 +335,9 @@ def run_gpu_arm(args):
             "roofline": {
                 "bound": "tensor", "kernel": "gemm_tc_kernel<BN> (all tcgen05 GEMM launches of one step)",
                 "achieved": achieved_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tf_sust"], "traffic": None,
+                "frac": achieved_tf / peaks["tf_sust"], "traffic": traffic,
+                "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM launches of one "
+                                 f"step ({traffic_src})") if traffic else None,
                 "launches_per_step": gemm_launches,
                 "algorithmic_flops_per_step": gemm_flops, "kernel_ms_per_step": gemm_ms,
                 "peak_source": "bf16 dense sustained, " + peaks["source"],
