@@ -132,6 +132,21 @@ int pf_q_sample(const float* x0, const float* noise, float* out, int64_t n, floa
 int pf_get_mask(const float* orig, float* mask, int32_t n_seg, int32_t seg_per_song, int32_t channels,
                 int32_t steps, int32_t pitches, int32_t above, pf_stream stream);
 
+/* Piano-roll decode (replaces the Python loops of utils.py:240-269
+ * prmat2c_to_prmat and the note loop of utils.py:446-470 prmat2c_to_midi_file).
+ * prmat2c [n_seg, channels >= 2, steps, pitches] fp32 (channel 0 onset, channel 1 sustain), device.
+ * prmat [n_seg * steps, pitches] int64, device: duration of the note starting at (step, pitch), 0
+ * where int(round(onset)) <= 0 -- the same bytes as the reference's (n_seg*ratio, n_step, 128)
+ * array.  Asynchronous on `stream`. */
+int pf_prmat2c_to_prmat(const float* prmat2c, int32_t n_seg, int32_t channels, int32_t steps,
+                        int32_t pitches, int64_t* prmat, pf_stream stream);
+/* Notes of a duration matrix in the reference's loop order (segment, step, pitch):
+ * row_offsets [rows + 1] int32 device scratch/out (exclusive offsets, total in the last slot),
+ * notes [cap][3] int32 device (row = seg * steps + step, pitch, duration; may be NULL with cap 0 to
+ * only count), *n_notes (host) receives the total.  Synchronises the stream. */
+int pf_prmat_notes(const int64_t* prmat, int64_t rows, int32_t pitches, int32_t* row_offsets,
+                   int32_t* notes, int64_t cap, int64_t* n_notes, pf_stream stream);
+
 /* Building-block ops (used by the parity tests; they allocate their own scratch and synchronise).
  * conv: x NHWC fp32 [B,H,W,Cin] (Cin%64==0), w [Cout,Cin,k,k] (k in {1,3}), stride in {1,2},
  * upsample in {0,1} (nearest 2x before the conv), bias/resid optional; out NHWC [B,Ho,Wo,Cout]. */

@@ -200,7 +200,51 @@ def make_mask_golden():
     save("mask_autoreg.npz", **out)
 
 
+def reference_utils_function(name):
+    """A pure-numpy function lifted from the reference's utils.py by ast (the module imports
+    pretty_midi / matplotlib at the top and cannot be imported here)."""
+    import ast
+
+    src = open(os.path.join(reference_loader.REFERENCE_ROOT, "utils.py")).read()
+    ns = {"np": np, "torch": torch}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            exec(compile(ast.Module([node], []), "utils.py", "exec"), ns)
+    return ns[name]
+
+
+def synthetic_prmat2c(n, T, seed):
+    """prmat2c-like tensor with the value classes the decode has to distinguish: exact 0 / 1, sampler
+    noise around them, the rounding boundaries 0.5 / 1.5 / 2.5, negatives, long sustains that run to
+    the end of the segment, sustain without onset."""
+    rng = np.random.default_rng(seed)
+    vals = np.asarray([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.3, 0.5, 0.5000001, 0.4999999, 0.6, 1.5, 2.5,
+                       -0.7, -0.5, 0.97, 1.02, 0.04], dtype=np.float32)
+    x = np.zeros((n, 2, T, 128), dtype=np.float32)
+    x[:, 0] = vals[rng.integers(0, len(vals), size=(n, T, 128))] * (rng.random((n, T, 128)) < 0.15)
+    x[:, 1] = vals[rng.integers(0, len(vals), size=(n, T, 128))] * (rng.random((n, T, 128)) < 0.6)
+    x[0, 0, 3, 60] = 1.0
+    x[0, 1, 4:, 60] = 1.0   # sustained to the end of the segment
+    x[0, 0, T - 1, 61] = 1.0  # onset on the last step
+    return x
+
+
+def make_decode_golden():
+    ref = reference_utils_function("prmat2c_to_prmat")
+    out = {}
+    for i, (n, T, seed) in enumerate([(3, 128, 11), (2, 64, 12), (1, 32, 13)]):
+        x = synthetic_prmat2c(n, T, seed)
+        out[f"case{i}_args"] = np.asarray([n, T, seed])
+        out[f"case{i}_prmat"] = ref(x).astype(np.int16)  # durations <= 128
+        out[f"case{i}_prmat_t"] = ref(torch.from_numpy(x)).astype(np.int16)  # Tensor input branch
+    save("decode.npz", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "decode":
+        os.makedirs(OUT, exist_ok=True)
+        make_decode_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "masks":
         os.makedirs(OUT, exist_ok=True)
         reference_loader.load()
@@ -208,3 +252,4 @@ if __name__ == "__main__":
     else:
         main()
         make_mask_golden()
+        make_decode_golden()

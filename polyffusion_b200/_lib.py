@@ -88,6 +88,11 @@ SYMBOLS = {
         c_int32,
         [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
     ),
+    "pf_prmat2c_to_prmat": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "pf_prmat_notes": (
+        c_int32,
+        [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_void_p],
+    ),
     "pf_op_conv2d_nhwc": (
         c_int32,
         [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,

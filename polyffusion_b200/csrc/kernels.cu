@@ -836,6 +836,115 @@ void launch_conv_out(const float* h, const double* stats, const float* gamma, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// prmat2c -> prmat / note list (reference utils.py:240-269 prmat2c_to_prmat and the note loop of
+// utils.py:446-470 prmat2c_to_midi_file).  Integer work, bit-exact:
+//   on(s, key)  = int(round(onset[s, key])) > 0      (Python round = half to even = rintf)
+//   dur(s, key) = 1 + number of consecutive steps s+1, s+2, .. < T with int(round(sustain)) > 0
+// One thread per (segment, key) column walks the T steps backwards carrying the sustain run length,
+// so consecutive threads touch consecutive keys (coalesced) and every cell is read once.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) prmat2c_dur_kernel(const float* __restrict__ x,
+                                                          long long* __restrict__ out, int N, int C, int T,
+                                                          int P) {
+  const long long idx = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * P) return;
+  const int n = static_cast<int>(idx / P), key = static_cast<int>(idx % P);
+  const float* on = x + (static_cast<long long>(n) * C + 0) * T * P + key;
+  const float* su = x + (static_cast<long long>(n) * C + 1) * T * P + key;
+  long long* o = out + static_cast<long long>(n) * T * P + key;
+  int run = 0;  // consecutive sustained steps starting at s + 1
+  for (int s = T - 1; s >= 0; --s) {
+    o[static_cast<long long>(s) * P] = (rintf(__ldg(on + static_cast<long long>(s) * P)) > 0.f) ? 1 + run : 0;
+    run = (rintf(__ldg(su + static_cast<long long>(s) * P)) > 0.f) ? run + 1 : 0;
+  }
+}
+void launch_prmat2c_dur(const float* x, long long* out, int N, int C, int T, int P, cudaStream_t s) {
+  const long long cols = static_cast<long long>(N) * P;
+  prmat2c_dur_kernel<<<static_cast<unsigned>((cols + 127) / 128), 128, 0, s>>>(x, out, N, C, T, P);
+}
+
+// note compaction in the reference's loop order (segment, step, key): per-row counts (warp per row,
+// ballots), exclusive scan of the row counts, ordered write of (row, key, dur) triples.
+__global__ void prmat_row_count_kernel(const long long* __restrict__ dur, int* __restrict__ counts,
+                                       long long rows, int P) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  int c = 0;
+  for (int k0 = 0; k0 < P; k0 += 32) {
+    const int k = k0 + lane;
+    const bool on = k < P && dur[row * P + k] > 0;
+    c += __popc(__ballot_sync(0xffffffffu, on));
+  }
+  if (lane == 0) counts[row] = c;
+}
+// single block, in place: counts[0 .. rows) -> exclusive offsets, counts[rows] = total
+__global__ void __launch_bounds__(1024) prmat_scan_kernel(int* __restrict__ counts, long long rows) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (long long base = 0; base < rows; base += 1024) {
+    const long long i = base + threadIdx.x;
+    const int v = i < rows ? counts[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int ws = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += t;
+      }
+      s_warp[lane] = ws;  // inclusive warp totals
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int excl = carry + (w ? s_warp[w - 1] : 0) + incl - v;
+    if (i < rows) counts[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[rows] = s_carry;
+}
+__global__ void prmat_write_notes_kernel(const long long* __restrict__ dur, const int* __restrict__ offsets,
+                                         int* __restrict__ notes, long long rows, int P, long long cap) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long pos = offsets[row];
+  for (int k0 = 0; k0 < P; k0 += 32) {
+    const int k = k0 + lane;
+    const long long d = k < P ? dur[row * P + k] : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, d > 0);
+    if (d > 0) {
+      const long long at = pos + __popc(m & ((1u << lane) - 1u));
+      if (at < cap) {
+        notes[at * 3 + 0] = static_cast<int>(row);
+        notes[at * 3 + 1] = k;
+        notes[at * 3 + 2] = static_cast<int>(d);
+      }
+    }
+    pos += __popc(m);
+  }
+}
+void launch_prmat_notes(const long long* dur, int* offsets, int* notes, long long rows, int P, long long cap,
+                        cudaStream_t s) {
+  const unsigned blocks = static_cast<unsigned>((rows * 32 + 255) / 256);
+  prmat_row_count_kernel<<<blocks, 256, 0, s>>>(dur, offsets, rows, P);
+  prmat_scan_kernel<<<1, 1024, 0, s>>>(offsets, rows);
+  if (notes && cap > 0) prmat_write_notes_kernel<<<blocks, 256, 0, s>>>(dur, offsets, notes, rows, P, cap);
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight packing / misc
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out_hi,

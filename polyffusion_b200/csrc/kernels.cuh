@@ -68,6 +68,13 @@ void launch_conv_out(const float* h, const double* stats, const float* gamma, co
                      float eps, const float* w, const float* bias, float* out, int B, int H, int W,
                      int C, int Cout, cudaStream_t s);
 
+// prmat2c [N, C>=2, T, P] fp32 (channel 0 onset, 1 sustain) -> note durations [N*T, P] int64
+// (reference utils.py:240-269); then (row, key, dur) triples in (segment, step, key) order:
+// offsets [rows + 1] receives the exclusive row offsets and the total, notes [cap][3] may be null
+void launch_prmat2c_dur(const float* x, long long* out, int N, int C, int T, int P, cudaStream_t s);
+void launch_prmat_notes(const long long* dur, int* offsets, int* notes, long long rows, int P, long long cap,
+                        cudaStream_t s);
+
 // weight packing: w [Cout, Cin, kh, kw] fp32 -> split bf16 [kh*kw][Cout_total][Cin] rows at row0
 // geglu_gran > 0: interleave the [x | gate] halves of a GeGLU projection in blocks of geglu_gran rows
 void launch_pack_weight(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin, int taps,

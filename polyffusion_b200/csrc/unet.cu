@@ -1476,6 +1476,33 @@ int pf_get_mask(const float* orig, float* mask, int32_t n_seg, int32_t seg_per_s
   });
 }
 
+int pf_prmat2c_to_prmat(const float* prmat2c, int32_t n_seg, int32_t channels, int32_t steps,
+                        int32_t pitches, int64_t* prmat, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(prmat2c && prmat && n_seg > 0 && channels >= 2 && steps > 0 && pitches > 0,
+             "bad prmat2c_to_prmat arguments");
+    launch_prmat2c_dur(prmat2c, reinterpret_cast<long long*>(prmat), n_seg, channels, steps, pitches,
+                       static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
+int pf_prmat_notes(const int64_t* prmat, int64_t rows, int32_t pitches, int32_t* row_offsets,
+                   int32_t* notes, int64_t cap, int64_t* n_notes, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(prmat && row_offsets && n_notes && rows > 0 && pitches > 0 && cap >= 0 &&
+                 rows * pitches < (1ll << 31),
+             "bad prmat_notes arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    launch_prmat_notes(reinterpret_cast<const long long*>(prmat), row_offsets, notes, rows, pitches, cap, s);
+    PF_CUDA(cudaGetLastError());
+    int total = 0;
+    PF_CUDA(cudaMemcpyAsync(&total, row_offsets + rows, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PF_CUDA(cudaStreamSynchronize(s));
+    *n_notes = total;
+  });
+}
+
 int pf_q_sample(const float* x0, const float* noise, float* out, int64_t n, float a, float b,
                 pf_stream stream) {
   return guarded([&] {
