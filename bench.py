@@ -185,6 +185,9 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION on these boxes) to stdout by default;
+        # stdout must carry exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from polyffusion_b200.sampler_sdf import SDFSampler
