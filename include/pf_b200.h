@@ -132,6 +132,26 @@ int pf_q_sample(const float* x0, const float* noise, float* out, int64_t n, floa
 int pf_get_mask(const float* orig, float* mask, int32_t n_seg, int32_t seg_per_song, int32_t channels,
                 int32_t steps, int32_t pitches, int32_t above, pf_stream stream);
 
+/* Condition encoders (the step before the sampling loop).  fp32,
+ * device pointers, asynchronous on `stream`, no allocation.
+ * pf_linear: out[r, :n_out] = act(in[r, :n_in] . weight[n_out, n_in]^T + bias)   (torch.nn.Linear;
+ *   act 0 = none, 1 = SiLU, 2 = exp as in `linear_var(x).exp_()`, dl_modules/chord_enc.py:20).
+ * pf_gru_bidir_last: final hidden states of a 1-layer bidirectional batch_first torch.nn.GRU
+ *   (`self.gru(x)[-1]` transposed to [B, 2H], forward half first: chord_enc.py:15-17,
+ *   txt_enc.py:29-31).  x [B, T, n_in]; w_ih[d] [3H, n_in], w_hh[d] [3H, H], b_ih[d], b_hh[d] [3H]
+ *   for d = 0 (forward), 1 (reverse), gate order r, z, n; h_last [B, 2H]. */
+int pf_linear(const float* in, int64_t ld_in, const float* weight, const float* bias, float* out,
+              int64_t ld_out, int32_t rows, int32_t n_out, int32_t n_in, int32_t act, pf_stream stream);
+size_t pf_gru_workspace_bytes(int32_t batch, int32_t steps, int32_t hidden);
+int pf_gru_bidir_last(const float* x, int32_t batch, int32_t steps, int32_t n_in, int32_t hidden,
+                      const float* const* w_ih, const float* const* w_hh, const float* const* b_ih,
+                      const float* const* b_hh, float* h_last, void* workspace, size_t workspace_bytes,
+                      pf_stream stream);
+/* TextureEncoder.cnn (txt_enc.py:10-14): Conv2d(1, channels, (4,12), stride (4,1)) -> ReLU ->
+ * MaxPool2d((1,4)) of pr [B, steps, pitches] -> out [B, channels, steps/4, (pitches-11)/4]. */
+int pf_txt_cnn(const float* pr, const float* weight, const float* bias, float* out, int32_t batch,
+               int32_t channels, int32_t steps, int32_t pitches, pf_stream stream);
+
 /* Piano-roll decode (replaces the Python loops of utils.py:240-269
  * prmat2c_to_prmat and the note loop of utils.py:446-470 prmat2c_to_midi_file).
  * prmat2c [n_seg, channels >= 2, steps, pitches] fp32 (channel 0 onset, channel 1 sustain), device.

@@ -229,6 +229,52 @@ def synthetic_prmat2c(n, T, seed):
     return x
 
 
+def reference_encoder_classes():
+    """RnnEncoder / TextureEncoder loaded by FILE PATH: the dl_modules package import fails on
+    pretty_midi (pianotree_dec.py), these two files are pure torch."""
+    import importlib.util
+
+    out = []
+    for fname, cls in (("chord_enc.py", "RnnEncoder"), ("txt_enc.py", "TextureEncoder")):
+        spec = importlib.util.spec_from_file_location(
+            "ref_" + fname[:-3], os.path.join(reference_loader.REFERENCE_ROOT, "dl_modules", fname))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        out.append(getattr(mod, cls))
+    return out
+
+
+def encoder_inputs():
+    """Synthetic chord matrices [B, 32, 36] (root one-hot | chroma multi-hot | bass one-hot, as
+    data/ chord features are laid out) and binary piano rolls [B, 128, 128]."""
+    g = torch.Generator().manual_seed(77)
+    B = 3
+    chord = torch.zeros(B, 32, 36)
+    for b in range(B):
+        for t in range(32):
+            chord[b, t, int(torch.randint(0, 12, (1,), generator=g))] = 1
+            chord[b, t, 12:24] = (torch.rand(12, generator=g) < 0.3).float()
+            chord[b, t, 24 + int(torch.randint(0, 12, (1,), generator=g))] = 1
+    prmat = (torch.rand(B, 128, 128, generator=g) < 0.03).float() * torch.randint(1, 9, (B, 128, 128), generator=g)
+    return chord, prmat
+
+
+def make_encoder_golden():
+    """Seeded random-init reference encoders at the sdf_chd8bar / sdf_txt sizes (no checkpoint is in
+    the tree): outputs of the real modules on the synthetic inputs."""
+    Rnn, Txt = reference_encoder_classes()
+    chord, prmat = encoder_inputs()
+    torch.manual_seed(5)
+    ce = Rnn(36, 512, 512).eval()
+    torch.manual_seed(6)
+    te = Txt(256, 1024, 256, 10).eval()
+    with torch.no_grad():
+        dc = ce(chord)
+        zs = [te(seg) for seg in prmat.split(32, 1)]
+    save("encoders.npz", chord_mu=dc.mean, chord_scale=dc.scale,
+         txt_mu=torch.stack([z.mean for z in zs], 1), txt_scale=torch.stack([z.scale for z in zs], 1))
+
+
 def make_decode_golden():
     ref = reference_utils_function("prmat2c_to_prmat")
     out = {}
@@ -245,6 +291,10 @@ if __name__ == "__main__":
         os.makedirs(OUT, exist_ok=True)
         make_decode_golden()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "encoders":
+        os.makedirs(OUT, exist_ok=True)
+        make_encoder_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "masks":
         os.makedirs(OUT, exist_ok=True)
         reference_loader.load()
@@ -253,3 +303,4 @@ if __name__ == "__main__":
         main()
         make_mask_golden()
         make_decode_golden()
+        make_encoder_golden()

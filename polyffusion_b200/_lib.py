@@ -88,6 +88,17 @@ SYMBOLS = {
         c_int32,
         [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
     ),
+    "pf_linear": (
+        c_int32,
+        [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    ),
+    "pf_gru_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "pf_gru_bidir_last": (
+        c_int32,
+        [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_void_p), POINTER(c_void_p),
+         POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
+    "pf_txt_cnn": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "pf_prmat2c_to_prmat": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "pf_prmat_notes": (
         c_int32,

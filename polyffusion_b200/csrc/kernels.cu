@@ -582,7 +582,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
   const int b = b0 + tb, n = n0 + tn;
   if (b < B && n < N) {
     acc += bias ? bias[n] : 0.f;
-    if (out_act) acc = silu_f(acc);
+    if (out_act == 1) acc = silu_f(acc);
+    else if (out_act == 2) acc = expf(acc);  // linear_var(.).exp_() of the condition encoders
     out[b * ld_out + n] = acc;
   }
 }
@@ -833,6 +834,60 @@ void launch_conv_out(const float* h, const double* stats, const float* gamma, co
                        static_cast<size_t>(Cout) * 9 * C + 2 * C) * sizeof(float);
   dim3 grid((W + CO_T - 1) / CO_T, (H + CO_T - 1) / CO_T, B);
   launch_pdl(conv_out_kernel, grid, dim3(256), smem, s, h, stats, gamma, beta, eps, w, bias, out, H, W, C, Cout);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Condition encoders (reference dl_modules/chord_enc.py:5-22 RnnEncoder, dl_modules/txt_enc.py:5-35
+// TextureEncoder): the step before the sampling loop.  fp32 throughout, precise expf / tanhf.
+// ------------------------------------------------------------------------------------------------
+// One GRU step (torch.nn.GRU gate order r, z, n):  gi = W_ih x_t + b_ih (row t of a [B, T, 3H]
+// tensor), gh = W_hh h + b_hh;  r = s(gi_r + gh_r), z = s(gi_z + gh_z), n = tanh(gi_n + r * gh_n),
+// h' = (1 - z) * n + z * h.
+__global__ void gru_cell_kernel(const float* __restrict__ gi, long long gi_ld, const float* __restrict__ gh,
+                                const float* __restrict__ h, float* __restrict__ h_out, long long out_ld,
+                                int B, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, j = i % H;
+  const float* gib = gi + b * gi_ld;
+  const float* ghb = gh + static_cast<long long>(b) * 3 * H;
+  const float r = 1.0f / (1.0f + expf(-(gib[j] + ghb[j])));
+  const float z = 1.0f / (1.0f + expf(-(gib[H + j] + ghb[H + j])));
+  const float n = tanhf(gib[2 * H + j] + r * ghb[2 * H + j]);
+  h_out[b * out_ld + j] = (1.0f - z) * n + z * h[static_cast<long long>(b) * H + j];
+}
+void launch_gru_cell(const float* gi, long long gi_ld, const float* gh, const float* h, float* h_out,
+                     long long out_ld, int B, int H, cudaStream_t s) {
+  gru_cell_kernel<<<(B * H + 255) / 256, 256, 0, s>>>(gi, gi_ld, gh, h, h_out, out_ld, B, H);
+}
+
+// TextureEncoder.cnn: Conv2d(1, C, (4, 12), stride (4, 1)) -> ReLU -> MaxPool2d((1, 4), (1, 4)) on a
+// [B, 32, 128] piano roll -> [B, C, 8, 29] (conv width 117, pooled 29).  One thread per output.
+__global__ void txt_cnn_kernel(const float* __restrict__ pr, const float* __restrict__ w,
+                               const float* __restrict__ bias, float* __restrict__ out, int B, int C, int T,
+                               int P) {
+  const int Ho = T / 4, Wc = P - 12 + 1, Wo = Wc / 4;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * C * Ho * Wo) return;
+  const int j = static_cast<int>(idx % Wo), i = static_cast<int>((idx / Wo) % Ho);
+  const int c = static_cast<int>((idx / (static_cast<long long>(Wo) * Ho)) % C);
+  const int b = static_cast<int>(idx / (static_cast<long long>(Wo) * Ho * C));
+  const float* in = pr + (static_cast<long long>(b) * T + 4 * i) * P;
+  const float* wc = w + c * 48;
+  float best = -INFINITY;
+  for (int jj = 0; jj < 4; ++jj) {
+    const int x = 4 * j + jj;
+    float acc = 0.f;
+    for (int ky = 0; ky < 4; ++ky)
+      for (int kx = 0; kx < 12; ++kx) acc = fmaf(in[ky * P + x + kx], wc[ky * 12 + kx], acc);
+    best = fmaxf(best, acc + bias[c]);
+  }
+  out[idx] = fmaxf(best, 0.f);
+}
+void launch_txt_cnn(const float* pr, const float* w, const float* bias, float* out, int B, int C, int T,
+                    int P, cudaStream_t s) {
+  const long long n = static_cast<long long>(B) * C * (T / 4) * ((P - 11) / 4);
+  txt_cnn_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(pr, w, bias, out, B, C, T, P);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -68,6 +68,12 @@ void launch_conv_out(const float* h, const double* stats, const float* gamma, co
                      float eps, const float* w, const float* bias, float* out, int B, int H, int W,
                      int C, int Cout, cudaStream_t s);
 
+// condition encoders: one GRU step, and TextureEncoder.cnn (conv (4,12)/(4,1) + ReLU + maxpool (1,4))
+void launch_gru_cell(const float* gi, long long gi_ld, const float* gh, const float* h, float* h_out,
+                     long long out_ld, int B, int H, cudaStream_t s);
+void launch_txt_cnn(const float* pr, const float* w, const float* bias, float* out, int B, int C, int T,
+                    int P, cudaStream_t s);
+
 // prmat2c [N, C>=2, T, P] fp32 (channel 0 onset, 1 sustain) -> note durations [N*T, P] int64
 // (reference utils.py:240-269); then (row, key, dur) triples in (segment, step, key) order:
 // offsets [rows + 1] receives the exclusive row offsets and the total, notes [cap][3] may be null

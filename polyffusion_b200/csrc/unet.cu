@@ -1476,6 +1476,68 @@ int pf_get_mask(const float* orig, float* mask, int32_t n_seg, int32_t seg_per_s
   });
 }
 
+int pf_linear(const float* in, int64_t ld_in, const float* weight, const float* bias, float* out,
+              int64_t ld_out, int32_t rows, int32_t n_out, int32_t n_in, int32_t act, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(in && weight && out && rows > 0 && n_out > 0 && n_in > 0 && act >= 0 && act <= 2,
+             "bad linear arguments");
+    launch_small_linear(in, ld_in, weight, bias, out, ld_out, rows, n_out, n_in, act,
+                        static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
+size_t pf_gru_workspace_bytes(int32_t batch, int32_t steps, int32_t hidden) {
+  // gi of both directions [2][B*T][3H], gh [B][3H], h ping-pong [2][B][H]
+  return (static_cast<size_t>(2) * batch * steps * 3 * hidden + static_cast<size_t>(batch) * 3 * hidden +
+          static_cast<size_t>(2) * batch * hidden) * sizeof(float);
+}
+
+int pf_gru_bidir_last(const float* x, int32_t batch, int32_t steps, int32_t n_in, int32_t hidden,
+                      const float* const* w_ih, const float* const* w_hh, const float* const* b_ih,
+                      const float* const* b_hh, float* h_last, void* workspace, size_t workspace_bytes,
+                      pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(x && w_ih && w_hh && b_ih && b_hh && h_last && workspace && batch > 0 && steps > 0 &&
+                 n_in > 0 && hidden > 0,
+             "bad gru arguments");
+    PF_CHECK(workspace_bytes >= pf_gru_workspace_bytes(batch, steps, hidden), "gru workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int B = batch, T = steps, H = hidden;
+    float* gi = static_cast<float*>(workspace);
+    float* gh = gi + static_cast<size_t>(2) * B * T * 3 * H;
+    float* hbuf = gh + static_cast<size_t>(B) * 3 * H;
+    for (int dir = 0; dir < 2; ++dir) {
+      float* gid = gi + static_cast<size_t>(dir) * B * T * 3 * H;
+      // input projections of every step at once: [B*T, n_in] x W_ih^T + b_ih
+      launch_small_linear(x, n_in, w_ih[dir], b_ih[dir], gid, 3 * H, B * T, 3 * H, n_in, 0, s);
+      float* h0 = hbuf;
+      float* h1 = hbuf + static_cast<size_t>(B) * H;
+      PF_CUDA(cudaMemsetAsync(h0, 0, static_cast<size_t>(B) * H * sizeof(float), s));
+      for (int k = 0; k < T; ++k) {
+        const int t = dir == 0 ? k : T - 1 - k;
+        launch_small_linear(h0, H, w_hh[dir], b_hh[dir], gh, 3 * H, B, 3 * H, H, 0, s);
+        const bool last = (k == T - 1);
+        // the final hidden state goes straight to its half of the [B, 2H] output (forward | backward)
+        launch_gru_cell(gid + static_cast<size_t>(t) * 3 * H, static_cast<long long>(T) * 3 * H, gh, h0,
+                        last ? h_last + dir * H : h1, last ? 2 * H : H, B, H, s);
+        std::swap(h0, h1);
+      }
+    }
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
+int pf_txt_cnn(const float* pr, const float* weight, const float* bias, float* out, int32_t batch,
+               int32_t channels, int32_t steps, int32_t pitches, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(pr && weight && bias && out && batch > 0 && channels > 0 && steps % 4 == 0 && pitches >= 15,
+             "bad txt_cnn arguments");
+    launch_txt_cnn(pr, weight, bias, out, batch, channels, steps, pitches, static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
 int pf_prmat2c_to_prmat(const float* prmat2c, int32_t n_seg, int32_t channels, int32_t steps,
                         int32_t pitches, int64_t* prmat, pf_stream stream) {
   return guarded([&] {
