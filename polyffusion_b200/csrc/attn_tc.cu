@@ -11,47 +11,72 @@
 // the true maximum: ONE bf16 product (hi*hi, K_lo is not even loaded) instead of three.  Pass 2 and
 // P V use the stacked-operand form of the split product (see gemm_tc.cu):
 //   Q_hi x [K_hi ; K_lo] (N = 128)  +  Q_lo x K_hi (N = 64, accumulated onto columns [0, 64))
-// so an S / O accumulator is 128 columns wide and the consumer adds its two halves.  Recomputing S
-// removes the accumulator-rescaling path of online softmax entirely.
+// so an S / O accumulator is 128 columns wide and the consumer adds its two halves.
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..9 =
-// softmax / epilogue (two warps per TMEM lane quarter, 32 key columns each).
-// TMEM: S double buffer (2 x 128 cols) + O (128 cols).  smem: Q, K ring, V^T ring, P double buffer
-// (written by the softmax warps in the UMMA K-major 128B-swizzled layout, consumed as the A operand).
+// Q and P live in TENSOR MEMORY as the A operands of their MMAs (tcgen05.mma with A in TMEM, lane =
+// row, one 32-bit column = two consecutive K elements, even one in the low half; checked on B200 with
+// tools/probe_umma_tmem_a.cu).  The previous version kept Q and P in shared memory and was bound by
+// shared-memory bandwidth: per key block the UMMA operand reads (136 KB), the P stores (32 KB) and
+// the TMA fills (40 KB) added up to ~1600 clk at 128 B/clk against ~900 clk of MMA work.  With A in
+// TMEM only K / V tiles go through shared memory (56 KB of reads + 40 KB of fills per key block).
+// The softmax warps write P_hi / P_lo of their own 16 keys straight back into the S columns they
+// just read (tcgen05.st), so the P V instruction of K-step ks finds its A slices at S + 16 ks (hi)
+// and S + 16 ks + 8 (lo).  Q is double buffered in TMEM and staged one work item ahead.
+// Measured alternatives that did NOT help (profiles/README.md): eight vs sixteen softmax warps,
+// three S accumulators with P in shared memory, four unstacked S/P buffers in TMEM -- the kernel
+// stays at ~290-305 us for N = Nk = 1024 at batch 64 (47 % tensor-pipe active): with ~230 warp
+// instructions per warp per key block the four schedulers are ~50 % busy issuing the softmax itself.
+//
+// Roles (576 threads): warp 0 = TMA producer (K, V^T rings), warp 1 = MMA issuer (+ TMEM allocator),
+// warps 2..17 = softmax / epilogue / Q staging (four warps per TMEM lane quarter, 16 columns each).
+// TMEM (512 columns): O [0,128)  S/P buffers [128,256) [256,384)  Q buffers [384,448) [448,512)
+// (each Q buffer: hi 32 columns, lo 32 columns).
 #include "common.cuh"
 #include "attn_tc.cuh"
 
 namespace pf {
 
-constexpr int AT_KS = 4;  // K ring stages
-constexpr int AT_VS = 3;  // V ring stages
-constexpr int AT_Q_BYTES = 128 * 128;       // 128 rows x 64 bf16
+constexpr int AT_KS = 6;  // K ring stages
+constexpr int AT_VS = 4;  // V ring stages
 constexpr int AT_KV_BYTES = 64 * 128;       // 64 rows x 64 bf16
-constexpr int AT_P_BYTES = 128 * 128;       // 128 rows x 64 keys bf16
-constexpr int AT_OFF_Q = 0;                                   // hi, lo
-constexpr int AT_OFF_K = AT_OFF_Q + 2 * AT_Q_BYTES;           // [KS][hi, lo]
+constexpr int AT_OFF_K = 0;                                   // [KS][hi, lo]
 constexpr int AT_OFF_V = AT_OFF_K + AT_KS * 2 * AT_KV_BYTES;  // [VS][hi, lo]
-constexpr int AT_OFF_P = AT_OFF_V + AT_VS * 2 * AT_KV_BYTES;  // [2][hi, lo]
-constexpr int AT_OFF_X = AT_OFF_P + 2 * 2 * AT_P_BYTES;       // float xch[2][128][2]
-constexpr int AT_SMEM = AT_OFF_X + 2 * 128 * 2 * 4;
+constexpr int AT_OFF_X = AT_OFF_V + AT_VS * 2 * AT_KV_BYTES;  // float xch[2][128][4]
+constexpr int AT_SMEM = AT_OFF_X + 2 * 128 * 4 * 4;
+constexpr int AT_SB = 2;  // S/P buffers (key blocks in flight)
+constexpr uint32_t TM_O = 0, TM_S = 128, TM_Q = 384;
 
 int attn_smem_bytes() { return AT_SMEM + 1024; }
 
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void umma_bf16_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_full, q_empty, o_full, o_empty;
+  __shared__ __align__(8) uint64_t q_full[2], q_empty[2], o_full, o_empty;
   __shared__ __align__(8) uint64_t k_full[AT_KS], k_empty[AT_KS], v_full[AT_VS], v_empty[AT_VS];
-  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2];
+  __shared__ __align__(8) uint64_t s_full[AT_SB], s_empty[AT_SB], p_full[AT_SB];
   __shared__ uint32_t tmem_base_s;
 
   constexpr uint32_t IDESC = umma_idesc_bf16(64);
   constexpr uint32_t IDESC2 = umma_idesc_bf16(128);
-  constexpr int TMEM_COLS = 512;  // S0 [0,128) S1 [128,256) O [256,384)
-  constexpr uint32_t O_COL = 256;
+  constexpr int TMEM_COLS = 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -60,22 +85,22 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
   const long long items = static_cast<long long>(p.B) * p.heads * nqt;
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&q_full), 1);
-    mbar_init(smem_u32(&q_empty), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&q_full[i]), 8);   // Q_hi: 4 warps (one per lane quarter), Q_lo: 4 warps
+      mbar_init(smem_u32(&q_empty[i]), 1);
+    }
+    for (int i = 0; i < AT_SB; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_empty[i]), 16);
+      mbar_init(smem_u32(&p_full[i]), 16);
+    }
     mbar_init(smem_u32(&o_full), 1);
-    mbar_init(smem_u32(&o_empty), 8);
+    mbar_init(smem_u32(&o_empty), 16);
     for (int i = 0; i < AT_KS; ++i) { mbar_init(smem_u32(&k_full[i]), 1); mbar_init(smem_u32(&k_empty[i]), 1); }
     for (int i = 0; i < AT_VS; ++i) { mbar_init(smem_u32(&v_full[i]), 1); mbar_init(smem_u32(&v_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&s_empty[i]), 8);
-      mbar_init(smem_u32(&p_full[i]), 8);
-      mbar_init(smem_u32(&p_empty[i]), 1);
-    }
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.q_hi); tma_prefetch_desc(&p.q_lo);
     tma_prefetch_desc(&p.k_hi); tma_prefetch_desc(&p.k_lo);
     tma_prefetch_desc(&p.v_hi); tma_prefetch_desc(&p.v_lo);
   }
@@ -93,16 +118,10 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      uint32_t kc = 0, vc = 0, it = 0;
-      for (long long w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-        const int qt = static_cast<int>(w % nqt);
+      uint32_t kc = 0, vc = 0;
+      for (long long w = blockIdx.x; w < items; w += gridDim.x) {
         const int bh = static_cast<int>(w / nqt);
         const int b = bh / p.heads, h = bh % p.heads;
-        mbar_wait(smem_u32(&q_empty), (it & 1u) ^ 1u);
-        mbar_expect_tx(smem_u32(&q_full), 2 * AT_Q_BYTES);
-        tma_load_2d(base + AT_OFF_Q, &p.q_hi, smem_u32(&q_full), p.qcol0 + h * 64, b * p.N + qt * 128);
-        tma_load_2d(base + AT_OFF_Q + AT_Q_BYTES, &p.q_lo, smem_u32(&q_full), p.qcol0 + h * 64,
-                    b * p.N + qt * 128);
         for (int pass = 0; pass < 2; ++pass) {
           for (int j = 0; j < nb; ++j) {
             {
@@ -132,115 +151,146 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      uint32_t kc = 0, vc = 0, sc = 0, pc = 0, it = 0;
-      const uint64_t dq_hi = umma_desc_sw128(base + AT_OFF_Q);
-      const uint64_t dq_lo = umma_desc_sw128(base + AT_OFF_Q + AT_Q_BYTES);
-      auto issue_s = [&](bool full) {
-        const uint32_t st = kc % AT_KS, kph = (kc / AT_KS) & 1u;
-        const uint32_t sb = sc & 1u, sph = (sc >> 1) & 1u;
-        mbar_wait(smem_u32(&k_full[st]), kph);
-        mbar_wait(smem_u32(&s_empty[sb]), sph ^ 1u);
-        tc_fence_after();
-        // K_hi (64 rows) is followed by K_lo (64 rows) in the stage: one 128-row B operand
-        const uint64_t dk_hi = umma_desc_sw128(base + AT_OFF_K + st * 2 * AT_KV_BYTES);
-        const uint32_t acc = tmem_base + sb * 128;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ko = static_cast<uint64_t>(k * 2);
-          if (full) {
-            umma_bf16(acc, dq_hi + ko, dk_hi + ko, IDESC2, k != 0);
-            umma_bf16(acc, dq_lo + ko, dk_hi + ko, IDESC, 1u);
-          } else {
-            umma_bf16(acc, dq_hi + ko, dk_hi + ko, IDESC, k != 0);
-          }
-        }
-        umma_commit(smem_u32(&k_empty[st]));
-        umma_commit(smem_u32(&s_full[sb]));
-        ++kc;
-        ++sc;
-      };
+      uint32_t kc = 0, vc = 0, sc = 0, it = 0;
+      uint32_t puse[AT_SB] = {0u, 0u};  // completed P phases per S/P buffer
       for (long long w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-        mbar_wait(smem_u32(&q_full), it & 1u);
+        const uint32_t qb = it & 1u;
+        mbar_wait(smem_u32(&q_full[qb]), (it >> 1) & 1u);
         tc_fence_after();
+        const uint32_t tq_hi = tmem_base + TM_Q + qb * 64, tq_lo = tq_hi + 32;
+        auto issue_s = [&](bool full) {
+          const uint32_t st = kc % AT_KS, kph = (kc / AT_KS) & 1u;
+          const uint32_t sb = sc % AT_SB, sph = (sc / AT_SB) & 1u;
+          mbar_wait(smem_u32(&k_full[st]), kph);
+          mbar_wait(smem_u32(&s_empty[sb]), sph ^ 1u);
+          tc_fence_after();
+          // K_hi (64 rows) is followed by K_lo (64 rows) in the stage: one 128-row B operand
+          const uint64_t dk_hi = umma_desc_sw128(base + AT_OFF_K + st * 2 * AT_KV_BYTES);
+          const uint32_t acc = tmem_base + TM_S + sb * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = static_cast<uint64_t>(k * 2);  // 32 bytes of B per K = 16 step
+            const uint32_t ka = static_cast<uint32_t>(k * 8);  // 8 TMEM columns of A per K = 16 step
+            if (full) {
+              umma_bf16_ta(acc, tq_hi + ka, dk_hi + ko, IDESC2, k != 0);
+              umma_bf16_ta(acc, tq_lo + ka, dk_hi + ko, IDESC, 1u);
+            } else {
+              umma_bf16_ta(acc, tq_hi + ka, dk_hi + ko, IDESC, k != 0);
+            }
+          }
+          umma_commit(smem_u32(&k_empty[st]));
+          umma_commit(smem_u32(&s_full[sb]));
+          ++kc;
+          ++sc;
+        };
         for (int j = 0; j < nb; ++j) issue_s(false);  // pass 1
-        issue_s(true);                                // pass 2, block 0
+        const int pre = nb < AT_SB ? nb : AT_SB;
+        const uint32_t sc2 = sc;                      // S counter of pass-2 block 0
+        for (int j = 0; j < pre; ++j) issue_s(true);  // pass 2 runs two key blocks ahead of P V
         for (int j = 0; j < nb; ++j) {
-          if (j + 1 < nb) issue_s(true);
-          const uint32_t pb = pc & 1u, pph = (pc >> 1) & 1u;
+          // P_j sits in the S buffer its scores came from
+          const uint32_t pb = (sc2 + static_cast<uint32_t>(j)) % AT_SB, pph = puse[pb] & 1u;
+          ++puse[pb];
           const uint32_t st = vc % AT_VS, vph = (vc / AT_VS) & 1u;
           mbar_wait(smem_u32(&p_full[pb]), pph);
           mbar_wait(smem_u32(&v_full[st]), vph);
           if (j == 0) mbar_wait(smem_u32(&o_empty), (it & 1u) ^ 1u);
           tc_fence_after();
-          const uint64_t dp_hi = umma_desc_sw128(base + AT_OFF_P + pb * 2 * AT_P_BYTES);
-          const uint64_t dp_lo = umma_desc_sw128(base + AT_OFF_P + pb * 2 * AT_P_BYTES + AT_P_BYTES);
           // V^T_hi (64 rows = d) followed by V^T_lo: one 128-row B operand
           const uint64_t dv_hi = umma_desc_sw128(base + AT_OFF_V + st * 2 * AT_KV_BYTES);
-          const uint32_t acc = tmem_base + O_COL;
+          const uint32_t acc = tmem_base + TM_O;
+          const uint32_t tp = tmem_base + TM_S + pb * 128;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ko = static_cast<uint64_t>(k * 2);
-            umma_bf16(acc, dp_hi + ko, dv_hi + ko, IDESC2, (j | k) != 0);
-            umma_bf16(acc, dp_lo + ko, dv_hi + ko, IDESC, 1u);
+            // keys 16k .. 16k+15 were written by the warps of column part k: hi at +16k, lo at +16k+8
+            umma_bf16_ta(acc, tp + 16 * k, dv_hi + ko, IDESC2, (j | k) != 0);
+            umma_bf16_ta(acc, tp + 16 * k + 8, dv_hi + ko, IDESC, 1u);
           }
-          umma_commit(smem_u32(&p_empty[pb]));
           umma_commit(smem_u32(&v_empty[st]));
-          ++pc;
           ++vc;
+          // the next scores for this buffer are issued behind P V (tcgen05 ops of one thread execute
+          // in order), so they cannot overwrite P before it has been consumed
+          if (j + pre < nb) issue_s(true);
         }
         umma_commit(smem_u32(&o_full));
-        umma_commit(smem_u32(&q_empty));
+        umma_commit(smem_u32(&q_empty[qb]));
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue warps
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;  // 0..3: which 16 columns of a 64-column block
     const int row = q * 32 + lane;
-    float* xch = reinterpret_cast<float*>(gbase + AT_OFF_X);
+    float* xch = reinterpret_cast<float*>(gbase + AT_OFF_X);  // [2][128][4]
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float c = p.scale_log2e;
-    uint32_t sc = 0, pc = 0, it = 0;
+    // Q row of work item w -> TMEM buffer (local item index & 1): part 0 stages hi, part 1 stages lo
+    auto stage_q = [&](long long w, uint32_t li) {
+      if (part >= 2) return;
+      const uint32_t qb = li & 1u;
+      const int qt = static_cast<int>(w % nqt);
+      const int bh = static_cast<int>(w / nqt);
+      const int b = bh / p.heads, h = bh % p.heads;
+      const __nv_bfloat16* src = (part == 0 ? p.q_hi_ptr : p.q_lo_ptr) +
+                                 (static_cast<long long>(b) * p.N + qt * 128 + row) * p.ldq + p.qcol0 + h * 64;
+      uint4 r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      mbar_wait(smem_u32(&q_empty[qb]), ((li >> 1) & 1u) ^ 1u);  // S MMAs of the buffer's last user are done
+      tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t v[8] = {r[2 * i].x, r[2 * i].y, r[2 * i].z, r[2 * i].w,
+                               r[2 * i + 1].x, r[2 * i + 1].y, r[2 * i + 1].z, r[2 * i + 1].w};
+        tmem_st8(lane_addr + TM_Q + qb * 64 + part * 32 + i * 8, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&q_full[qb]));
+    };
+    uint32_t sc = 0, it = 0;
     for (long long w = blockIdx.x; w < items; w += gridDim.x, ++it) {
       const int qt = static_cast<int>(w % nqt);
       const int bh = static_cast<int>(w / nqt);
       const int b = bh / p.heads, h = bh % p.heads;
+      if (it == 0) stage_q(w, 0);
+      if (w + gridDim.x < items) stage_q(w + gridDim.x, it + 1);  // one work item ahead
       // ---- pass 1: row maximum
       float mx = -INFINITY;
       for (int j = 0; j < nb; ++j, ++sc) {
-        const uint32_t sb = sc & 1u, sph = (sc >> 1) & 1u;
+        const uint32_t sb = sc % AT_SB, sph = (sc / AT_SB) & 1u;
         mbar_wait(smem_u32(&s_full[sb]), sph);
         tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(lane_addr + sb * 128 + half * 32, v);
+        uint32_t v[16];
+        tmem_ld16(lane_addr + TM_S + sb * 128 + part * 16, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_empty[sb]));
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
-      xch[row * 2 + half] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float m = fmaxf(xch[row * 2], xch[row * 2 + 1]);
+      xch[row * 4 + part] = mx;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      const float4 m4 = *reinterpret_cast<const float4*>(xch + row * 4);
+      const float m = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
       const float mc = m * c;
-      // ---- pass 2: probabilities -> P (smem, UMMA layout), row sums
+      // ---- pass 2: probabilities -> P (TMEM, over the S columns just read), row sums
       float sum = 0.f;
-      for (int j = 0; j < nb; ++j, ++sc, ++pc) {
-        const uint32_t sb = sc & 1u, sph = (sc >> 1) & 1u;
-        const uint32_t pb = pc & 1u, pph = (pc >> 1) & 1u;
+      for (int j = 0; j < nb; ++j, ++sc) {
+        const uint32_t sb = sc % AT_SB, sph = (sc / AT_SB) & 1u;
         mbar_wait(smem_u32(&s_full[sb]), sph);
         tc_fence_after();
-        uint32_t v[32], v2[32];
-        tmem_ld32(lane_addr + sb * 128 + half * 32, v);
-        tmem_ld32(lane_addr + sb * 128 + 64 + half * 32, v2);
+        const uint32_t sbuf = lane_addr + TM_S + sb * 128 + part * 16;
+        uint32_t v[16], v2[16];
+        tmem_ld16(sbuf, v);
+        tmem_ld16(sbuf + 64, v2);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_empty[sb]));
-        uint32_t ph[16], pl[16];
+        uint32_t ph[8], pl[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const float s0 = __uint_as_float(v[2 * i]) + __uint_as_float(v2[2 * i]);
           const float s1 = __uint_as_float(v[2 * i + 1]) + __uint_as_float(v2[2 * i + 1]);
           const float p0 = fast_ex2(fmaf(s0, c, -mc));
@@ -248,41 +298,40 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
           sum += p0 + p1;
           split2(p0, p1, ph[i], pl[i]);
         }
-        mbar_wait(smem_u32(&p_empty[pb]), pph ^ 1u);
-        uint8_t* prow = gbase + AT_OFF_P + pb * 2 * AT_P_BYTES + row * 128;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int chunk = ((half * 4 + i) ^ (row & 7)) << 4;
-          *reinterpret_cast<uint4*>(prow + chunk) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-          *reinterpret_cast<uint4*>(prow + AT_P_BYTES + chunk) =
-              make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
-        }
-        fence_proxy_async_smem();
+        // this warp's own 16 S columns become P_hi (8 columns) | P_lo (8 columns)
+        tmem_st8(sbuf, ph);
+        tmem_st8(sbuf + 8, pl);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&p_full[pb]));
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&s_empty[sb]));
+          mbar_arrive(smem_u32(&p_full[sb]));  // P_j lives in S buffer sb
+        }
       }
-      xch[256 + row * 2 + half] = sum;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float inv = 1.0f / (xch[256 + row * 2] + xch[256 + row * 2 + 1]);
-      // ---- epilogue: O / l -> split-bf16 [B*N, ldo] at columns h*64 + half*32
+      xch[512 + row * 4 + part] = sum;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      const float4 l4 = *reinterpret_cast<const float4*>(xch + 512 + row * 4);
+      const float inv = 1.0f / ((l4.x + l4.y) + (l4.z + l4.w));
+      // ---- epilogue: O / l -> split-bf16 [B*N, ldo] at columns h*64 + part*16
       mbar_wait(smem_u32(&o_full), it & 1u);
       tc_fence_after();
-      uint32_t o[32];
+      uint32_t o[16];
       {
-        uint32_t o2[32];
-        tmem_ld32(lane_addr + O_COL + half * 32, o);
-        tmem_ld32(lane_addr + O_COL + 64 + half * 32, o2);
+        uint32_t o2[16];
+        tmem_ld16(lane_addr + TM_O + part * 16, o);
+        tmem_ld16(lane_addr + TM_O + 64 + part * 16, o2);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) + __uint_as_float(o2[i]));
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) + __uint_as_float(o2[i]));
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&o_empty));
       const long long off =
-          (static_cast<long long>(b) * p.N + qt * 128 + row) * p.ldo + p.ocol0 + h * 64 + half * 32;
+          (static_cast<long long>(b) * p.N + qt * 128 + row) * p.ldo + p.ocol0 + h * 64 + part * 16;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         uint4 hh, ll;
         split2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv, hh.x, ll.x);
         split2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv, hh.y, ll.y);

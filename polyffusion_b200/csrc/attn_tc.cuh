@@ -7,10 +7,13 @@
 
 namespace pf {
 
-constexpr int ATTN_THREADS = 320;
+constexpr int ATTN_THREADS = 576;  // warp0 TMA, warp1 MMA, warps 2..17 softmax / epilogue
 
 struct alignas(64) AttnParams {
-  CUtensorMap q_hi, q_lo;  // split-bf16 queries, 2-D {ldq, B*N}, box {64, 128}
+  CUtensorMap q_hi, q_lo;  // (unused since Q is staged through registers into TMEM; kept for layout stability)
+  const __nv_bfloat16* q_hi_ptr;  // split-bf16 queries [B*N, ldq], head h at columns qcol0 + h*64
+  const __nv_bfloat16* q_lo_ptr;
+  long long ldq;
   CUtensorMap k_hi, k_lo;  // split-bf16 keys,    2-D {ldk, B*Nk}, box {64, 64}
   CUtensorMap v_hi, v_lo;  // split-bf16 V^T,     2-D {Nk, B*heads*64}, box {64, 64}
   int B, heads, N, Nk;     // N % 128 == 0, Nk % 64 == 0, d_head == 64

@@ -645,6 +645,7 @@ struct Builder {
         a.v_hi = make_map_2d(vt.hi, Nk, static_cast<long long>(Z) * 64, 64);
         a.v_lo = make_map_2d(vt.lo, Nk, static_cast<long long>(Z) * 64, 64);
       }
+      a.q_hi_ptr = q.hi; a.q_lo_ptr = q.lo; a.ldq = ldq;
       a.B = B; a.heads = heads; a.N = N; a.Nk = Nk;
       a.qcol0 = qcol0; a.kcol0 = kcol0; a.ocol0 = 0;
       a.scale_log2e = 0.125f * 1.4426950408889634f;  // d_head ** -0.5 (unet_attention.py:157) * log2(e)
