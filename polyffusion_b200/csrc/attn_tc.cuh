@@ -10,8 +10,7 @@ namespace pf {
 constexpr int ATTN_THREADS = 576;  // warp0 TMA, warp1 MMA, warps 2..17 softmax / epilogue
 
 struct alignas(64) AttnParams {
-  CUtensorMap q_hi, q_lo;  // (unused since Q is staged through registers into TMEM; kept for layout stability)
-  const __nv_bfloat16* q_hi_ptr;  // split-bf16 queries [B*N, ldq], head h at columns qcol0 + h*64
+  const __nv_bfloat16* q_hi_ptr;  // split-bf16 queries [B*N, ldq], head h at columns qcol0 + h*64 (staged into TMEM)
   const __nv_bfloat16* q_lo_ptr;
   long long ldq;
   CUtensorMap k_hi, k_lo;  // split-bf16 keys,    2-D {ldk, B*Nk}, box {64, 64}

@@ -638,8 +638,6 @@ struct Builder {
       Op& op = push(OP_ATTN);
       AttnParams& a = op.a;
       if (!dry) {
-        a.q_hi = make_map_2d(q.hi, ldq, static_cast<long long>(B) * N, 128);
-        a.q_lo = make_map_2d(q.lo, ldq, static_cast<long long>(B) * N, 128);
         a.k_hi = make_map_2d(k.hi, ldk, static_cast<long long>(B) * Nk, 64);
         a.k_lo = make_map_2d(k.lo, ldk, static_cast<long long>(B) * Nk, 64);
         a.v_hi = make_map_2d(vt.hi, Nk, static_cast<long long>(Z) * 64, 64);
