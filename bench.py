@@ -345,6 +345,9 @@ def run_gpu_arm(args):
                 "algorithmic_flops_per_step": gemm_flops, "kernel_ms_per_step": gemm_ms,
                 "peak_source": "bf16 dense sustained, " + peaks["source"],
                 "issued_frac": 3 * achieved_tf / peaks["tf_sust"],
+                # the whole step (GEMMs + attention + HBM-bound transforms + step epilogue) on the same scale
+                "whole_step_frac": GFLOP_PER_SAMPLE_EVAL * B / 1e3 / (ms_per_step / 1e3) / peaks["tf_sust"],
+                "whole_step_issued_frac": 3 * GFLOP_PER_SAMPLE_EVAL * B / 1e3 / (ms_per_step / 1e3) / peaks["tf_sust"],
             },
         }
         if cpu_value is not None:
