@@ -184,10 +184,13 @@ def run_gpu_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # stdout must carry exactly ONE JSON line, but NCCL prints its version banner there (C-level
+    # printf, NCCL_DEBUG_FILE does not move it): point fd 1 at stderr for the whole run and keep a
+    # private handle on the real stdout for the result line
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL prints its version banner (NCCL_DEBUG=VERSION on these boxes) to stdout by default;
-        # stdout must carry exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from polyffusion_b200.sampler_sdf import SDFSampler
@@ -355,7 +358,8 @@ def run_gpu_arm(args):
                 "value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "3 DDPM reverse steps at batch 4 (1 warm-up), oracle port of the reference PyTorch CPU path, all host threads",
             }
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
