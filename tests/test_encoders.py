@@ -121,3 +121,25 @@ def test_gpu_texture_encoder_matches_reference():
     assert z.shape == (3, 1, 1024)
     ok, err = close(z, eo.encode_txt(sd, prmat))
     assert ok, f"encode_txt max abs err {err}"
+
+
+def test_cond_glue_batching_matches_reference_segment_loop():
+    """cond.encode_txt runs the four 32-step segments as ONE batch; the reference loops over segments
+    and concatenates (model_sdf.py:153-164).  Host logic only: a CPU stand-in encoder built on the
+    oracle shows the reshapes put every segment's latent in the reference's position."""
+    from types import SimpleNamespace
+
+    from oracle import encoder_oracle as eo
+    from oracle.make_golden import encoder_inputs
+    from polyffusion_b200.cond import encode_chord, encode_txt
+
+    chord, prmat = encoder_inputs()
+    ce, te = build()
+    sdc, sdt = ce.state_dict(), te.state_dict()
+    fake_txt = lambda pr: SimpleNamespace(mean=eo.texture_encoder(sdt, pr)[0])
+    fake_chd = lambda ch: SimpleNamespace(mean=eo.chord_encoder(sdc, ch)[0])
+    assert torch.allclose(encode_txt(fake_txt, prmat), eo.encode_txt(sdt, prmat), atol=1e-6)
+    assert torch.equal(encode_chord(fake_chd, chord), eo.encode_chord(sdc, chord))
+    # without encoders: the reference's pass-through / flatten branches
+    assert encode_txt(None, prmat) is prmat
+    assert encode_chord(None, chord).shape == (3, 1, 32 * 36)
