@@ -752,17 +752,21 @@ __global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict_
   __syncthreads();
   const int x = threadIdx.x & 127, co = threadIdx.x >> 7;
   const float bco = __ldg(bias + co);
+  // the raw values of input row r + 1 are fetched into registers while row r is being reduced
+  float4 a[8];
+  auto fetch = [&](int r) {
+    const float4* src = reinterpret_cast<const float4*>(h + (static_cast<long long>(b) * H + r) * W * 64);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = threadIdx.x + 256 * u;
+      a[u] = (idx < W * 16) ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (y0 - 1 >= 0) fetch(y0 - 1);
   for (int r = y0 - 1; r <= y1; ++r) {
     const int slot = (r + 3) % 3;
     const bool inside = (r >= 0 && r < H);
     if (inside) {
-      const float4* src = reinterpret_cast<const float4*>(h + (static_cast<long long>(b) * H + r) * W * 64);
-      float4 a[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int idx = threadIdx.x + 256 * u;
-        a[u] = (idx < W * 16) ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int idx = threadIdx.x + 256 * u;
@@ -775,6 +779,7 @@ __global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict_
         *reinterpret_cast<float4*>(st + pix * CO2_PITCH + c) = v;
       }
     }
+    if (r + 1 <= y1 && r + 1 >= 0 && r + 1 < H) fetch(r + 1);
     __syncthreads();
     float acc[9];
 #pragma unroll
