@@ -110,6 +110,8 @@ def test_install_dropin_aliases_reference_import_paths():
         assert unet_mod.UNetModel is polyffusion_b200.stable_diffusion.model.unet.UNetModel
         assert importlib.import_module("sampler_sdf").SDFSampler.__module__ == "polyffusion_b200.sampler_sdf"
         assert hasattr(importlib.import_module("ddpm"), "DenoiseDiffusion")
+        assert importlib.import_module("dl_modules.chord_enc").RnnEncoder.__module__ == "polyffusion_b200.dl_modules.chord_enc"
+        assert importlib.import_module("dl_modules.txt_enc").TextureEncoder.__module__ == "polyffusion_b200.dl_modules.txt_enc"
     finally:
         for k, v in saved.items():
             if v is None:
