@@ -29,13 +29,48 @@ _DROPIN_MODULES = {
 }
 
 
-def install_dropin() -> None:
-    """Alias the reference's top-level module names (``stable_diffusion.model.unet``, ``sampler_sdf``,
+# alias packages that replace only PART of a reference package: their __path__ is extended with the
+# reference's own directory so that every submodule this package does not provide still resolves
+_DROPIN_PACKAGES = ("stable_diffusion", "stable_diffusion.model", "stable_diffusion.sampler", "ddpm")
+
+
+def _reference_dirs(pkg: str, reference_dir=None):
+    """Directories named like the package `pkg` (dotted) below the reference checkout(s): the explicit
+    `reference_dir` (the reference's ``polyffusion/`` directory) and every ``sys.path`` entry."""
+    import os
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    rel = os.path.join(*pkg.split("."))
+    roots = ([reference_dir] if reference_dir else []) + [p or os.getcwd() for p in sys.path]
+    out = []
+    for root in roots:
+        d = os.path.join(root, rel)
+        if os.path.isdir(d) and not os.path.abspath(d).startswith(here) and d not in out:
+            out.append(d)
+    return out
+
+
+def install_dropin(reference_dir=None) -> None:
+    """Alias the reference's module names (``stable_diffusion.model.unet``, ``sampler_sdf``,
     ``sampler_ddim``, ``ddpm`` ...) to this package in ``sys.modules``, so that the reference's own
-    ``inference_sdf.py`` / ``models/model_sdf.py`` imports resolve to the CUDA implementation.
-    Call it before importing the reference scripts."""
+    ``inference_sdf.py`` / ``inference.py`` / ``models/model_sdf.py`` / ``train/*.py`` imports resolve
+    to the CUDA implementation.  Call it before importing the reference scripts, with the reference's
+    ``polyffusion/`` directory on ``sys.path`` (it is ``sys.path[0]`` when its scripts run) or passed
+    as ``reference_dir``.
+
+    Only what this package implements is replaced.  The alias packages keep the reference's own
+    directories on their ``__path__``, so modules this package does not provide --
+    ``stable_diffusion.util``, ``stable_diffusion.model.autoencoder``, ``stable_diffusion.losses``,
+    ``stable_diffusion.sampler.ddim`` / ``.ddpm``, ``ddpm.sampling`` / ``.training`` -- import from
+    the reference unchanged (and see the drop-in classes through their relative imports)."""
     import importlib
     import sys
 
     for alias, target in _DROPIN_MODULES.items():
-        sys.modules[alias] = importlib.import_module(target)
+        mod = importlib.import_module(target)
+        sys.modules[alias] = mod
+        if alias in _DROPIN_PACKAGES:
+            for d in _reference_dirs(alias, reference_dir):
+                if d not in mod.__path__:
+                    mod.__path__.append(d)

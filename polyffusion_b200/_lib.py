@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpf_b200.so")
+# PF_B200_LIB selects a variant build of the same sources (A/B measurements, csrc/Makefile)
+LIB_PATH = os.environ.get("PF_B200_LIB") or os.path.join(_HERE, "libpf_b200.so")
 
 
 class PfError(RuntimeError):

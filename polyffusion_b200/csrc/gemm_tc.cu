@@ -12,6 +12,15 @@
 namespace pf {
 
 constexpr int MAX_STAGES = 8;
+// Register budget: __launch_bounds__(GEMM_LB_THREADS, 1).  320 lets ptxas use up to 204 registers (it
+// takes 162-168).  Building with -DPF_GEMM_LB_THREADS=512 caps the kernels at 128 registers so that
+// operand-transform blocks of the other half-batch lane (unet.cu, PF_LANE_MIN_HW) can be co-resident;
+// measured on B200 (profiles/r3a_lanes_ab.txt): the cap costs 0.9 ms per step and the overlap buys
+// nothing because the step is limited by board power, so it is off by default.
+#ifndef PF_GEMM_LB_THREADS
+#define PF_GEMM_LB_THREADS 320
+#endif
+constexpr int GEMM_LB_THREADS = PF_GEMM_LB_THREADS;
 constexpr int STG_FLOATS = 32 * 32;  // per-warp staging tile: 32 rows x 32 fp32, 16-byte groups XOR-swizzled by row
 
 struct TileCoord {
@@ -491,26 +500,26 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
 }
 
 template <int BN, int MODE, bool STATS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(GEMM_LB_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, false, MODE, STATS, false, false>(p);
 }
 
 template <int BN, int MODE, bool STATS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, true, MODE, STATS, false, false>(p);
 }
 
 // cta_group::2 with the stacked [B_hi ; B_lo] operand (BN <= 128)
 template <int BN, int MODE, bool STATS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
     gemm_tc2s_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, true, MODE, STATS, true, false>(p);
 }
 
 // stacked B + halo stages (one 130-pixel A row serves the three dx taps); fp32 output only
 template <int BN, bool STATS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
     gemm_tc2h_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, true, OUT_F32, STATS, true, true>(p);
 }

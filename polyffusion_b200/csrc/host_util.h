@@ -57,6 +57,11 @@ class Arena {
   void* alloc(size_t bytes);
   void free(void* p);
   size_t peak() const { return peak_; }
+  // true if p is the start of a live block of this arena
+  bool owns(const void* p) const {
+    const char* c = static_cast<const char*>(p);
+    return c >= base_ && live_.count(static_cast<size_t>(c - base_)) != 0;
+  }
 
  private:
   char* base_;

@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
   const bool norm = a.stats0 != nullptr;
   if (norm) {
     const int cpg = C / a.groups;
-    for (int c = threadIdx.x; c < C; c += 256) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const int g = c / cpg;
       double ts = 0.0, tq = 0.0;
       for (int i = 0; i < cpg; ++i) {
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
   const long long pix_base = static_cast<long long>(b) * HW;
 #pragma unroll 1
   for (int k = 0; k < AS_IPT; ++k) {
-    const int item = (blockIdx.x * AS_IPT + k) * 256 + threadIdx.x;
+    const int item = (blockIdx.x * AS_IPT + k) * blockDim.x + threadIdx.x;
     if (item >= items) break;
     const int c = (item % c16n) * 16;
     const int pl = item / c16n;  // pixel inside the sample
@@ -329,8 +329,11 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
 void launch_act_split(const ActSplitArgs& a, cudaStream_t s) {
   const int C = a.C0 + a.C1;
   const long long items = static_cast<long long>(a.H) * a.W * (C >> 4);
-  dim3 grid(static_cast<unsigned>((items + 256 * AS_IPT - 1) / (256 * AS_IPT)), a.B);
-  launch_pdl(act_split_kernel, grid, dim3(256), 0, s, a);
+  // PF_ACT_THREADS=128: blocks small enough (64 registers per thread) to sit beside a register-capped
+  // GEMM CTA in the half-batch lane experiment (unet.cu); 256 is the measured best otherwise
+  static const int threads = std::getenv("PF_ACT_THREADS") ? std::atoi(std::getenv("PF_ACT_THREADS")) : 256;
+  dim3 grid(static_cast<unsigned>((items + threads * AS_IPT - 1) / (threads * AS_IPT)), a.B);
+  launch_pdl(act_split_kernel, grid, dim3(threads), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -72,6 +72,8 @@ struct Op {
   void* o[2] = {nullptr, nullptr};
   long long i[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float f = 0.f;
+  int lane = -1;          // -1: whole batch on the caller's stream; 0 / 1: half-batch lane (see Builder)
+  long long ext_off = 0;  // element offset into the external tensor (lane 1 starts half a batch in)
 };
 
 struct Plan {
@@ -79,6 +81,7 @@ struct Plan {
   void* workspace = nullptr;
   size_t bytes = 0;
   std::vector<Op> ops;
+  bool has_lanes = false;
 };
 
 }  // namespace pf
@@ -100,6 +103,11 @@ struct pf_unet {
   pf::Plan* last_plan = nullptr;
   cudaStream_t pack_stream = nullptr;
   bool packing = false;
+  // second stream + fork/join events for the half-batch lanes (created lazily, never destroyed while
+  // the handle lives; events are only ordering markers, timing disabled)
+  cudaStream_t side_stream = nullptr;
+  std::vector<cudaEvent_t> lane_events;
+  size_t lane_event_next = 0;
 };
 
 namespace pf {
@@ -337,12 +345,26 @@ struct T {  // fp32 NHWC activation
   Split sp;
 };
 
+// Half-batch lanes.  The high-resolution ends of the UNet (no attention, few channels) alternate an
+// HBM-bound operand transform with a tensor-bound GEMM; the two cannot overlap inside one sample
+// chain.  Those sections are therefore built TWICE, once per half of the batch ("lane" 0 / 1), and
+// replayed on two streams: while lane 0's GEMM owns the tensor pipes, lane 1's transform blocks are
+// resident beside it on the same SMs (the GEMM kernels are capped at 128 registers for that purpose)
+// and stream through HBM.  Block outputs are allocated ONCE at full batch size from the main arena
+// (lane 1 writes the second half), scratch comes from a private arena per lane, and main-arena frees
+// inside a section are deferred to its join so that a lane running ahead never overwrites memory the
+// other lane still reads.
 struct Builder {
   pf_unet* m;
   Plan* plan;
   Arena arena;
+  Arena lane_arena[2];
   bool dry;
   int B, n_cond;
+  int lane = -1;
+  std::vector<std::pair<char*, size_t>> out_fifo;  // full-size outputs allocated by lane 0, consumed by lane 1
+  size_t out_fifo_head = 0;
+  std::vector<void*> deferred_free;
   double* gn_pool = nullptr;
   size_t gn_pool_doubles = 0, gn_used = 0;
   const float* emb_all = nullptr;  // [B, emb_total]
@@ -351,12 +373,32 @@ struct Builder {
   int st_index = 0;
   const float* cond_ext = nullptr;
 
-  Builder(pf_unet* m_, Plan* p_, char* base, bool dry_, int B_, int nc)
-      : m(m_), plan(p_), arena(base), dry(dry_), B(B_), n_cond(nc) {}
+  Builder(pf_unet* m_, Plan* p_, char* base, bool dry_, int B_, int nc, char* lane0 = nullptr,
+          char* lane1 = nullptr)
+      : m(m_), plan(p_), arena(base), lane_arena{Arena(lane0 ? lane0 : reinterpret_cast<char*>(1ull << 40)),
+                                                 Arena(lane1 ? lane1 : reinterpret_cast<char*>(2ull << 40))},
+        dry(dry_), B(B_), n_cond(nc) {}
 
+  // scratch: private to the lane that is being built (main arena outside the lane sections)
   template <class X>
   X* alloc(size_t count) {
-    return static_cast<X*>(arena.alloc(count * sizeof(X)));
+    Arena& a = lane >= 0 ? lane_arena[lane] : arena;
+    return static_cast<X*>(a.alloc(count * sizeof(X)));
+  }
+  // block output: `count` elements per lane; one full-batch allocation shared by both lanes
+  template <class X>
+  X* alloc_out(size_t count) {
+    const size_t bytes = count * sizeof(X);
+    if (lane < 0) return static_cast<X*>(arena.alloc(bytes));
+    if (lane == 0) {
+      char* p = static_cast<char*>(arena.alloc(2 * bytes));
+      out_fifo.emplace_back(p, bytes);
+      return reinterpret_cast<X*>(p);
+    }
+    PF_CHECK(out_fifo_head < out_fifo.size() && out_fifo[out_fifo_head].second == bytes,
+             "lane 1 does not replay lane 0's output allocations");
+    char* p = out_fifo[out_fifo_head++].first;
+    return reinterpret_cast<X*>(p + bytes);
   }
   Split alloc_split(size_t count) {
     Split s;
@@ -364,15 +406,33 @@ struct Builder {
     s.lo = alloc<bf16>(count);
     return s;
   }
+  Split alloc_split_out(size_t count) {
+    Split s;
+    s.hi = alloc_out<bf16>(count);
+    s.lo = alloc_out<bf16>(count);
+    return s;
+  }
+  void afree(void* p) {
+    if (!p) return;
+    if (lane < 0) {
+      arena.free(p);
+    } else if (lane_arena[lane].owns(p)) {
+      lane_arena[lane].free(p);
+    } else if (lane == 0) {
+      PF_CHECK(arena.owns(p), "arena: free of unknown block inside a lane section");
+      deferred_free.push_back(p);  // released at the join
+    }  // lane 1: the second half of a block lane 0 accounts for
+  }
   void free_split(Split& s) {
-    arena.free(s.hi);
-    arena.free(s.lo);
+    afree(s.hi);
+    afree(s.lo);
     s.hi = s.lo = nullptr;
   }
   Op& push(OpKind k) {
     plan->ops.emplace_back();
     Op& op = plan->ops.back();
     op.kind = k;
+    op.lane = lane;
     memset(&op.g, 0, sizeof op.g);
     memset(&op.a, 0, sizeof op.a);
     memset(&op.as, 0, sizeof op.as);
@@ -381,9 +441,16 @@ struct Builder {
 
   // ---------------------------------------------------------------- elementwise emitters
   double* new_stats(int C) {
+    const size_t n = static_cast<size_t>(B) * C * 2;  // B = samples of this lane
+    if (lane == 1) {
+      PF_CHECK(out_fifo_head < out_fifo.size() && out_fifo[out_fifo_head].second == n * sizeof(double),
+               "lane 1 does not replay lane 0's statistics allocations");
+      return reinterpret_cast<double*>(out_fifo[out_fifo_head++].first) + n;
+    }
     double* acc = gn_pool + gn_used;
-    gn_used += static_cast<size_t>(B) * C * 2;
+    gn_used += (lane == 0 ? 2 : 1) * n;
     PF_CHECK(dry || gn_used <= gn_pool_doubles, "GN statistics pool overflow");
+    if (lane == 0) out_fifo.emplace_back(reinterpret_cast<char*>(acc), n * sizeof(double));
     return acc;
   }
 
@@ -596,12 +663,12 @@ struct Builder {
     }
     free_split(a1);
     Split a2 = act_split(h1, nullptr, L.name + ".out_layers.0", 1e-5f, true, XF_SAME);
-    arena.free(h1.p);
+    afree(h1.p);
     T y;
     y.C = L.cout; y.H = H; y.W = Wd;
-    if (split_only) y.sp = alloc_split(npix * L.cout);
+    if (split_only) y.sp = alloc_split_out(npix * L.cout);
     else {
-      y.p = alloc<float>(npix * L.cout);
+      y.p = alloc_out<float>(npix * L.cout);
       y.stats = new_stats(L.cout);
     }
     PackedW& w2 = W(m, L.name + ".out_layers.3.weight", {L.name + ".out_layers.3.weight"});
@@ -699,7 +766,7 @@ struct Builder {
       op.i[0] = static_cast<long long>(Z) * N; op.i[1] = Nk;
       op.f = 0.125f;  // d_head ** -0.5 with d_head = 64 (unet_attention.py:157)
     }
-    arena.free(S);
+    afree(S);
     {
       Op& op = push(OP_GEMM);
       op.bn = 64;
@@ -832,6 +899,7 @@ struct Builder {
         ct.C = c.d_cond; ct.H = 1; ct.W = n_cond;
         Split cs = act_split(ct, nullptr, "", 0.f, false, XF_SAME);
         plan->ops.back().ext = EXT_COND;
+        plan->ops.back().ext_off = ext_lane_off(static_cast<long long>(n_cond) * c.d_cond);
         const long long crow = static_cast<long long>(B) * n_cond;
         Split k2 = alloc_split(crow * C);
         Split v2t = alloc_split(crow * C);
@@ -856,10 +924,10 @@ struct Builder {
         Op& op2 = conv_gemm(s2, W(m, tb + ".attn2.to_out.0.weight", {}), nullptr, nullptr, H, Wd, C);
         out_f32(op2, x2, C, F(m, tb + ".attn2.to_out.0.bias"), 0, x1, C);
         free_split(o2);
-        arena.free(x1);
+        afree(x1);
         xattn = x2;
       }
-      arena.free(t0);
+      afree(t0);
       // ---- feed forward: x = ff(norm3(x)) + x   (GeGLU, unet_attention.py:296-333)
       Split l3 = ln_split(xattn, rows, C, tb + ".norm3");
       const int Fh = 4 * C;
@@ -895,7 +963,7 @@ struct Builder {
         }
       }
       free_split(e);
-      arena.free(xattn);
+      afree(xattn);
       t0 = x3;
     }
     // proj_out + residual
@@ -906,10 +974,10 @@ struct Builder {
       Op& op = conv_gemm(s, W(m, L.name + ".proj_out.weight", {L.name + ".proj_out.weight"}), nullptr,
                          nullptr, H, Wd, C, 0, 0, !split_only);
       if (split_only) {
-        y.sp = alloc_split(rows * C);
+        y.sp = alloc_split_out(rows * C);
         out_split(op, y.sp, C, F(m, L.name + ".proj_out.bias"), 0, x.p, C);
       } else {
-        y.p = alloc<float>(rows * C);
+        y.p = alloc_out<float>(rows * C);
         y.stats = new_stats(C);
         out_f32(op, y.p, C, F(m, L.name + ".proj_out.bias"), 0, x.p, C, y.stats);
       }
@@ -923,7 +991,7 @@ struct Builder {
     Split a = act_split(x, nullptr, "", 0.f, false, XF_S2D);
     T y;
     y.C = x.C; y.H = x.H / 2; y.W = x.W / 2;
-    y.p = alloc<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
+    y.p = alloc_out<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
     ASrc s{a, x.C, y.W, y.H, 4 * B, 2};
     Op& op = conv_gemm(s, W(m, L.name + ".op.weight", {L.name + ".op.weight"}), nullptr, nullptr, y.H,
                        y.W, y.C);
@@ -939,7 +1007,7 @@ struct Builder {
     Split a = x.sp.hi ? x.sp : act_split(x, nullptr, "", 0.f, false, XF_SAME);
     T y;
     y.C = x.C; y.H = x.H * 2; y.W = x.W * 2;
-    y.p = alloc<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
+    y.p = alloc_out<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
     y.stats = new_stats(y.C);
     PackedW& w = W_up(m, L.name + ".conv.weight");
     for (int par = 0; par < 4; ++par) {
@@ -1050,7 +1118,7 @@ struct Builder {
         small_linear(cvall, nv, wo, bo, cv, nv, d_attn, d_attn, 0, EXT_NONE, ng);
         cross_cv = cv;
         cross_cv_ld = nv;
-        arena.free(cvall);
+        afree(cvall);
       }
     }
     // ---- blocks
@@ -1068,10 +1136,11 @@ struct Builder {
         switch (l.kind) {
           case Layer::CONV_IN: {
             nxt.C = l.cout; nxt.H = H; nxt.W = Wd;
-            nxt.p = alloc<float>(static_cast<size_t>(B) * H * Wd * l.cout);
+            nxt.p = alloc_out<float>(static_cast<size_t>(B) * H * Wd * l.cout);
             PF_CHECK(l.cout % 16 == 0, "first conv: channels must be a multiple of 16");
             Op& op = push(OP_CONV_IN);
             op.ext = EXT_X;
+            op.ext_off = ext_lane_off(static_cast<long long>(l.cin) * H * Wd);
             op.p[1] = F(m, l.name + ".weight"); op.p[2] = F(m, l.name + ".bias");
             op.o[0] = nxt.p;
             op.i[0] = B; op.i[1] = l.cin; op.i[2] = H; op.i[3] = Wd; op.i[4] = l.cout;
@@ -1088,53 +1157,241 @@ struct Builder {
           case Layer::UP: nxt = up_sample(l, cur); break;
         }
         // free the consumed input unless it is the block input (owned by the caller)
-        if (!first) arena.free(cur.p);
+        if (!first) afree(cur.p);
         cur = nxt;
         first = false;
       }
       return cur;
     };
-    for (size_t bi = 0; bi < m->input_blocks.size(); ++bi) {
-      T y = run_block(m->input_blocks[bi], x, nullptr);
-      // the block input stays alive only if it is a saved skip (it always is, except before block 0)
-      x = y;
-      skips.push_back(y);
+    // ---- lane sections: maximal runs of attention-free blocks whose input has >= lane_min_hw pixels
+    // off by default: measured slower on B200 (profiles/r3a_lanes_ab.txt); PF_LANE_MIN_HW=4096 splits
+    // the 128x128 and 64x64 levels
+    static const int lane_min_hw = std::getenv("PF_LANE_MIN_HW") ? std::atoi(std::getenv("PF_LANE_MIN_HW")) : 0;
+    const bool lanes_ok = lane_min_hw > 0 && B % 2 == 0 && B >= 2;
+    auto splittable = [&](const BlockSpec& b, int hin, int win) {
+      if (!lanes_ok || static_cast<long long>(hin) * win < lane_min_hw) return false;
+      for (auto& l : b.layers)
+        if (l.kind == Layer::ST) return false;
+      return true;
+    };
+    auto out_conv = [&](const T& xf) {
+      // ---- out: GroupNorm + SiLU + conv3x3 -> NCHW (unet.py:145-149, 196)
+      PF_CHECK(c.out_channels <= 4, "out_channels > 4 unsupported by the final conv kernel");
+      PF_CHECK(xf.C % 32 == 0, "final GroupNorm: channels %d not divisible by 32", xf.C);
+      const double* st = stats_of(xf);
+      Op& op = push(OP_CONV_OUT);
+      op.ext = EXT_OUT;
+      op.ext_off = ext_lane_off(static_cast<long long>(c.out_channels) * H * Wd);
+      op.p[0] = xf.p; op.p[1] = st; op.p[2] = F(m, "out.0.weight"); op.p[3] = F(m, "out.2.weight");
+      op.p[4] = F(m, "out.2.bias"); op.p[5] = F(m, "out.0.bias");
+      op.f = 1e-5f;
+      op.i[0] = B; op.i[1] = H; op.i[2] = Wd; op.i[3] = xf.C; op.i[4] = c.out_channels;
+    };
+
+    // down path
+    {
+      int hin = H, win = Wd;
+      size_t bi = 0;
+      const size_t nb = m->input_blocks.size();
+      auto out_dims = [&](const BlockSpec& b, int& h, int& w) {
+        for (auto& l : b.layers) {
+          if (l.kind == Layer::DOWN) { h /= 2; w /= 2; }
+          if (l.kind == Layer::UP) { h *= 2; w *= 2; }
+        }
+      };
+      while (bi < nb) {
+        if (splittable(m->input_blocks[bi], hin, win)) {
+          size_t be = bi;
+          int h2 = hin, w2 = win;
+          while (be < nb && splittable(m->input_blocks[be], h2, w2)) {
+            out_dims(m->input_blocks[be], h2, w2);
+            ++be;
+          }
+          const T xfull = x;
+          std::vector<T> outs = run_lanes([&]() {
+            std::vector<T> ys;
+            T xl = lane_view(xfull);
+            for (size_t k = bi; k < be; ++k) {
+              xl = run_block(m->input_blocks[k], xl, nullptr);
+              ys.push_back(xl);
+            }
+            return ys;
+          });
+          for (auto& y : outs) skips.push_back(y);
+          x = outs.back();
+          hin = h2; win = w2;
+          bi = be;
+        } else {
+          T y = run_block(m->input_blocks[bi], x, nullptr);
+          // the block input stays alive only if it is a saved skip (it always is, except before block 0)
+          x = y;
+          skips.push_back(y);
+          out_dims(m->input_blocks[bi], hin, win);
+          ++bi;
+        }
+      }
     }
     {
       T y = run_block(m->middle, x, nullptr);
       // x (== skips.back()) is still needed as a skip
       x = y;
     }
-    bool x_is_skip = false;
-    for (size_t bi = 0; bi < m->output_blocks.size(); ++bi) {
-      T skip = skips.back();
-      skips.pop_back();
-      T y = run_block(m->output_blocks[bi], x, &skip);
-      if (!x_is_skip) arena.free(x.p);
-      arena.free(skip.p);
-      x = y;
-    }
-    // ---- out: GroupNorm + SiLU + conv3x3 -> NCHW (unet.py:145-149, 196)
+    // up path (+ the final conv when the last blocks run in lanes)
+    bool out_done = false;
     {
-      PF_CHECK(c.out_channels <= 4, "out_channels > 4 unsupported by the final conv kernel");
-      PF_CHECK(x.C % 32 == 0, "final GroupNorm: channels %d not divisible by 32", x.C);
-      const double* st = stats_of(x);
-      Op& op = push(OP_CONV_OUT);
-      op.ext = EXT_OUT;
-      op.p[0] = x.p; op.p[1] = st; op.p[2] = F(m, "out.0.weight"); op.p[3] = F(m, "out.2.weight");
-      op.p[4] = F(m, "out.2.bias"); op.p[5] = F(m, "out.0.bias");
-      op.f = 1e-5f;
-      op.i[0] = B; op.i[1] = H; op.i[2] = Wd; op.i[3] = x.C; op.i[4] = c.out_channels;
+      size_t bi = 0;
+      const size_t nb = m->output_blocks.size();
+      while (bi < nb) {
+        if (splittable(m->output_blocks[bi], x.H, x.W)) {
+          size_t be = bi;
+          int h2 = x.H, w2 = x.W;
+          while (be < nb && splittable(m->output_blocks[be], h2, w2)) {
+            for (auto& l : m->output_blocks[be].layers)
+              if (l.kind == Layer::UP) { h2 *= 2; w2 *= 2; }
+            ++be;
+          }
+          const T xfull = x;
+          const bool with_out = (be == nb);
+          std::vector<T> sk(skips.end() - static_cast<long>(be - bi), skips.end());
+          skips.resize(skips.size() - (be - bi));
+          std::vector<T> outs = run_lanes([&]() {
+            T xl = lane_view(xfull);
+            for (size_t k = bi; k < be; ++k) {
+              T skl = lane_view(sk[sk.size() - 1 - (k - bi)]);
+              T y = run_block(m->output_blocks[k], xl, &skl);
+              afree(xl.p);
+              afree(skl.p);
+              xl = y;
+            }
+            if (with_out) out_conv(xl);
+            return std::vector<T>{xl};
+          });
+          x = outs.back();
+          out_done = with_out;
+          bi = be;
+        } else {
+          T skip = skips.back();
+          skips.pop_back();
+          T y = run_block(m->output_blocks[bi], x, &skip);
+          afree(x.p);
+          afree(skip.p);
+          x = y;
+          ++bi;
+        }
+      }
     }
+    if (!out_done) out_conv(x);
+  }
+
+  // ---------------------------------------------------------------- lanes
+  static size_t up1k(size_t v) { return (v + 1023) / 1024 * 1024; }
+  size_t main_bytes() const { return up1k(arena.peak()); }
+  size_t lane_bytes() const { return up1k(std::max(lane_arena[0].peak(), lane_arena[1].peak())); }
+  size_t total_bytes() const { return main_bytes() + 2 * lane_bytes(); }
+  long long ext_lane_off(long long per_sample) const {
+    return lane == 1 ? static_cast<long long>(B) * per_sample : 0;
+  }
+  // this lane's half of a full-batch tensor (identity outside the lane sections)
+  T lane_view(const T& full) const {
+    T v = full;
+    if (lane != 1) return v;
+    const size_t n = static_cast<size_t>(B) * full.H * full.W * full.C;
+    if (v.p) v.p += n;
+    if (v.sp.hi) { v.sp.hi += n; v.sp.lo += n; }
+    if (v.stats) v.stats += static_cast<size_t>(B) * full.C * 2;
+    return v;
+  }
+  // Build `body` once per lane (half batch each) and interleave the two op lists; returns lane 0's
+  // results, whose pointers are the full-batch tensors.
+  template <class Fn>
+  std::vector<T> run_lanes(Fn&& body) {
+    PF_CHECK(lane < 0 && B % 2 == 0, "nested lane section");
+    const int Bfull = B;
+    const float* emb_full = emb_all;
+    const float* cv_full = cross_cv;
+    const float* cond_full = cond_ext;
+    const size_t op0 = plan->ops.size();
+    out_fifo.clear();
+    out_fifo_head = 0;
+    std::vector<T> res;
+    size_t op1 = op0;
+    for (int ln = 0; ln < 2; ++ln) {
+      lane = ln;
+      B = Bfull / 2;
+      emb_all = emb_full ? emb_full + static_cast<size_t>(ln) * B * m->emb_total : nullptr;
+      cross_cv = cv_full ? cv_full + static_cast<size_t>(ln) * B * cross_cv_ld : nullptr;
+      cond_ext = cond_full ? cond_full + static_cast<size_t>(ln) * B * n_cond * m->cfg.d_cond : nullptr;
+      std::vector<T> r = body();
+      if (ln == 0) {
+        res = r;
+        op1 = plan->ops.size();
+      }
+    }
+    PF_CHECK(out_fifo_head == out_fifo.size(), "lane 1 did not consume every output of lane 0");
+    lane = -1;
+    B = Bfull;
+    emb_all = emb_full;
+    cross_cv = cv_full;
+    cond_ext = cond_full;
+    // interleave: a0 b0 a1 b1 ... (issue order of the two streams)
+    {
+      std::vector<Op> a(plan->ops.begin() + op0, plan->ops.begin() + op1);
+      std::vector<Op> b(plan->ops.begin() + op1, plan->ops.end());
+      plan->ops.resize(op0);
+      for (size_t i = 0; i < std::max(a.size(), b.size()); ++i) {
+        if (i < a.size()) plan->ops.push_back(a[i]);
+        if (i < b.size()) plan->ops.push_back(b[i]);
+      }
+    }
+    plan->has_lanes = true;
+    for (void* p : deferred_free) arena.free(p);
+    deferred_free.clear();
+    return res;
   }
 };
 
 // =================================================================================== execution
+static cudaEvent_t next_lane_event(pf_unet* m) {
+  if (m->lane_events.empty()) {
+    m->lane_events.resize(16);
+    for (auto& e : m->lane_events) PF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  return m->lane_events[m->lane_event_next++ % m->lane_events.size()];
+}
+
+// Lane ops (Op::lane 0 / 1) run on two streams: lane 0 stays on the caller's stream, lane 1 goes to
+// the handle's side stream, forked / joined with events (legal under stream capture: the side stream
+// joins the capture at the fork and returns to the origin stream at the join).  With `events` (the
+// profiled run) everything is serialised on the caller's stream so that per-launch times add up.
 static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, const float* cond,
-                     float* out, cudaStream_t s, std::vector<cudaEvent_t>* events = nullptr) {
+                     float* out, cudaStream_t main_stream, std::vector<cudaEvent_t>* events = nullptr) {
   size_t opi = 0;
+  static const bool lanes_serial = std::getenv("PF_LANES_SERIAL") != nullptr;
+  const bool use_side = plan.has_lanes && !events && !lanes_serial;
+  if (use_side && !m->side_stream)
+    PF_CUDA(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+  bool forked = false;
+  auto join = [&]() {
+    if (!forked) return;
+    cudaEvent_t e = next_lane_event(m);
+    PF_CUDA(cudaEventRecord(e, m->side_stream));
+    PF_CUDA(cudaStreamWaitEvent(main_stream, e, 0));
+    forked = false;
+  };
   for (Op& op : plan.ops) {
-    if (events) PF_CUDA(cudaEventRecord((*events)[opi++], s));
+    if (events) PF_CUDA(cudaEventRecord((*events)[opi++], main_stream));
+    cudaStream_t s = main_stream;
+    if (use_side) {
+      if (op.lane >= 0 && !forked) {
+        cudaEvent_t e = next_lane_event(m);
+        PF_CUDA(cudaEventRecord(e, main_stream));
+        PF_CUDA(cudaStreamWaitEvent(m->side_stream, e, 0));
+        forked = true;
+      } else if (op.lane < 0) {
+        join();
+      }
+      if (op.lane == 1) s = m->side_stream;
+    }
     switch (op.kind) {
       case OP_MEMSET:
         PF_CUDA(cudaMemsetAsync(op.o[0], 0, static_cast<size_t>(op.i[0]), s));
@@ -1146,7 +1403,7 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
         PF_CUDA(launch_gemm(op.g, op.bn, m->num_sms, s));
         break;
       case OP_CONV_IN:
-        launch_conv_in(x, static_cast<const float*>(op.p[1]), static_cast<const float*>(op.p[2]),
+        launch_conv_in(x + op.ext_off, static_cast<const float*>(op.p[1]), static_cast<const float*>(op.p[2]),
                        static_cast<float*>(op.o[0]), static_cast<double*>(op.o[1]), (int)op.i[0],
                        (int)op.i[1], (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
         break;
@@ -1158,7 +1415,7 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
         break;  // (retired: GroupNorm is finalised inside the operand transform / final conv)
       case OP_ACT_SPLIT: {
         ActSplitArgs a = op.as;
-        if (op.ext == EXT_COND) a.src0 = cond;
+        if (op.ext == EXT_COND) a.src0 = cond + op.ext_off;
         launch_act_split(a, s);
         break;
       }
@@ -1188,12 +1445,13 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
       case OP_CONV_OUT:
         launch_conv_out(static_cast<const float*>(op.p[0]), static_cast<const double*>(op.p[1]),
                         static_cast<const float*>(op.p[2]), static_cast<const float*>(op.p[5]), op.f,
-                        static_cast<const float*>(op.p[3]), static_cast<const float*>(op.p[4]), out,
-                        (int)op.i[0], (int)op.i[1], (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
+                        static_cast<const float*>(op.p[3]), static_cast<const float*>(op.p[4]),
+                        out + op.ext_off, (int)op.i[0], (int)op.i[1], (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
         break;
     }
   }
-  if (events) PF_CUDA(cudaEventRecord((*events)[opi], s));
+  join();
+  if (events) PF_CUDA(cudaEventRecord((*events)[opi], main_stream));
   PF_CUDA(cudaGetLastError());
 }
 
@@ -1253,6 +1511,8 @@ int pf_unet_create(const pf_unet_cfg* cfg, pf_unet** out) {
 
 void pf_unet_destroy(pf_unet* h) {
   if (!h) return;
+  for (auto& e : h->lane_events) cudaEventDestroy(e);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   for (void* p : h->owned) cudaFree(p);
   delete h;
 }
@@ -1307,7 +1567,7 @@ size_t pf_unet_workspace_bytes(pf_unet* h, int32_t batch, int32_t n_cond, int32_
     Builder b(h, &scratch, reinterpret_cast<char*>(4096), true, batch, n_cond);
     b.cond_ext = nullptr;
     b.build(height, width);
-    bytes = b.arena.peak();
+    bytes = b.total_bytes();
   });
   return rc == 0 ? bytes : 0;
 }
@@ -1373,10 +1633,21 @@ static Plan* get_plan(pf_unet* h, const float* cond, int32_t batch, int32_t n_co
       std::unique_ptr<Plan> np(new Plan());
       np->B = batch; np->n_cond = n_cond; np->H = height; np->W = width;
       np->workspace = workspace;
-      Builder b(h, np.get(), static_cast<char*>(workspace), false, batch, n_cond);
+      // dry pass first: the lane arenas sit behind the main arena, whose peak is only known afterwards
+      size_t main_peak = 0, lane_peak = 0;
+      {
+        Plan scratch;
+        Builder d(h, &scratch, reinterpret_cast<char*>(4096), true, batch, n_cond);
+        d.build(height, width);
+        main_peak = d.main_bytes();
+        lane_peak = d.lane_bytes();
+      }
+      char* base = static_cast<char*>(workspace);
+      Builder b(h, np.get(), base, false, batch, n_cond, base + main_peak, base + main_peak + lane_peak);
       b.cond_ext = cond;
       b.build(height, width);
-      np->bytes = b.arena.peak();
+      PF_CHECK(b.main_bytes() == main_peak && b.lane_bytes() == lane_peak, "plan build is not reproducible");
+      np->bytes = b.total_bytes();
       PF_CHECK(np->bytes <= workspace_bytes, "workspace too small: need %zu bytes, got %zu", np->bytes,
                workspace_bytes);
       if (h->plans.size() >= 8) h->plans.erase(h->plans.begin());
