@@ -174,6 +174,29 @@ int pf_op_conv2d_nhwc(const float* x, int32_t B, int32_t H, int32_t W, int32_t C
                       int32_t Cout, int32_t ksize, int32_t stride, int32_t upsample,
                       const float* bias, const float* resid, float* out, int32_t force_bn,
                       pf_stream stream);
+/* Same, with a per-sample epilogue vector: bias [B, bias_ld] when bias_ld > 0 (e.g. conv bias +
+ * time-embedding projection, ddpm/unet.py:140-141), a shared bias [Cout] when bias_ld == 0. */
+int pf_op_conv2d_nhwc_ex(const float* x, int32_t B, int32_t H, int32_t W, int32_t Cin, const float* w,
+                         int32_t Cout, int32_t ksize, int32_t stride, int32_t upsample,
+                         const float* bias, int64_t bias_ld, const float* resid, float* out,
+                         int32_t force_bn, pf_stream stream);
+/* Generic blocks of the legacy unconditional UNet (ddpm/unet.py:410-444, SURVEY.md section 8a row D2;
+ * composed by polyffusion_b200/ddpm/unet.py).  All asynchronous on `stream`.
+ * groupnorm: GroupNorm(groups, eps) [+ Swish] of an NHWC fp32 tensor, any C % groups == 0
+ *            (ResidualBlock norms with 32 groups up to C = 2048, final GroupNorm(8, 64), ddpm/unet.py:404);
+ * softmax_rows: out[r, :] = softmax(scale * s[r, :]) (AttentionBlock, ddpm/unet.py:199-201);
+ * time_sincos: [sin(t f_i) | cos(t f_i)] with t cast to fp32 (TimeEmbedding, ddpm/unet.py:62-72). */
+int pf_op_groupnorm_generic(const float* x, int32_t B, int32_t HW, int32_t C, int32_t groups,
+                            const float* gamma, const float* beta, float eps, int32_t silu, float* out,
+                            pf_stream stream);
+int pf_op_softmax_rows(const float* s, float scale, float* out, int64_t rows, int32_t n, pf_stream stream);
+int pf_op_time_sincos(const int64_t* t, const float* freqs, float* out, int32_t B, int32_t half,
+                      pf_stream stream);
+/* direct fp32 3x3 convolution, pad 1, w [Cout,Cin,3,3]: the legacy UNet's edge layers (image_proj from
+ * NCHW, final to NCHW; ddpm/unet.py:345-347, 405-407); x / out are NCHW or NHWC per the two flags. */
+int pf_op_conv3x3_direct(const float* x, const float* w, const float* bias, float* out, int32_t B,
+                         int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t in_nchw, int32_t out_nchw,
+                         pf_stream stream);
 /* softmax(q k^T / sqrt(d_head)) v per head: q [B,N,heads*64], k/v [B,Nk,heads*64] fp32 -> out
  * [B,N,heads*64] fp32 (unet_attention.py:261-293 normal_attention, before to_out). */
 int pf_op_attention(const float* q, const float* k, const float* v, int32_t B, int32_t N,

@@ -286,7 +286,32 @@ def make_decode_golden():
     save("decode.npz", **out)
 
 
+def make_legacy_unet_golden():
+    """BASELINE config 1 with the REAL legacy eps-model: ddpm.unet.UNet(2, 64, [1,2,2,4], [F,F,F,T])
+    (params/ddpm.yaml:13-27; 167.8 M parameters, seeded init), one evaluation at four timesteps and
+    DenoiseDiffusion.p_sample over 10 reverse steps (999..990) at B = 4 with taped noise, on the CPU."""
+    ref = reference_loader.load()
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    unet = ref.UNet(2, 64, [1, 2, 2, 4], [False, False, False, True]).eval()
+    g = torch.Generator().manual_seed(61)
+    x = torch.randn(4, 2, 128, 128, generator=g)
+    t = torch.tensor([999, 500, 3, 250])
+    with torch.no_grad():
+        eps = unet(x, t)
+    dd = ref.DenoiseDiffusion(unet, 1000)
+    xx = x
+    with Tape(62), torch.no_grad():
+        for ti in range(999, 989, -1):
+            xx = dd.p_sample(xx, xx.new_full((4,), ti, dtype=torch.long))
+    save("legacy_unet.npz", x=x, t=t, eps=eps, seed=0, tape_seed=62, out=xx)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "legacy_unet":
+        os.makedirs(OUT, exist_ok=True)
+        make_legacy_unet_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "decode":
         os.makedirs(OUT, exist_ok=True)
         make_decode_golden()
@@ -304,3 +329,4 @@ if __name__ == "__main__":
         make_mask_golden()
         make_decode_golden()
         make_encoder_golden()
+        make_legacy_unet_golden()

@@ -3,7 +3,7 @@
 Drop-in module surface (same import paths below this package as below the reference's
 ``polyffusion/`` directory): ``stable_diffusion.model.unet.UNetModel``,
 ``stable_diffusion.latent_diffusion.LatentDiffusion``, ``stable_diffusion.sampler.DiffusionSampler``,
-``sampler_sdf.SDFSampler``, ``sampler_ddim.DDIMSampler``, ``ddpm.DenoiseDiffusion``,
+``sampler_sdf.SDFSampler``, ``sampler_ddim.DDIMSampler``, ``ddpm.DenoiseDiffusion``, ``ddpm.unet.UNet``,
 ``dl_modules.chord_enc.RnnEncoder``, ``dl_modules.txt_enc.TextureEncoder``; plus ``autoreg``, ``cond``
 and ``utils`` (song-batched autoregressive driver, condition glue, piano-roll decode).
 All arithmetic runs in hand-written CUDA kernels behind the C ABI in ``include/pf_b200.h``.
@@ -21,6 +21,8 @@ _DROPIN_MODULES = {
     "sampler_sdf": "polyffusion_b200.sampler_sdf",
     "sampler_ddim": "polyffusion_b200.sampler_ddim",
     "ddpm": "polyffusion_b200.ddpm",
+    "ddpm.unet": "polyffusion_b200.ddpm.unet",
+    "ddpm.utils": "polyffusion_b200.ddpm.utils",
     # only the two encoder SUBMODULES: the reference's dl_modules/__init__.py then picks them up through
     # its own `from .chord_enc import RnnEncoder as ChordEncoder` / `from .txt_enc import TextureEncoder`
     # (the decoders and PianoTree modules stay the reference's)

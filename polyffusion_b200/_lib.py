@@ -110,6 +110,22 @@ SYMBOLS = {
         [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
          c_void_p, c_void_p, c_void_p, c_int32, c_void_p],
     ),
+    "pf_op_conv2d_nhwc_ex": (
+        c_int32,
+        [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
+         c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p],
+    ),
+    "pf_op_groupnorm_generic": (
+        c_int32,
+        [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p],
+    ),
+    "pf_op_softmax_rows": (c_int32, [c_void_p, c_float, c_void_p, c_int64, c_int32, c_void_p]),
+    "pf_op_time_sincos": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "pf_op_conv3x3_direct": (
+        c_int32,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+         c_void_p],
+    ),
     "pf_op_attention": (
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p],

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include <cstdlib>
@@ -264,6 +265,67 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- fp16 + fp8 ("f16f8") operands
+// Second precision scheme of the GEMM kernels (gemm_tc.cuh): x = h16 + lo with h16 = rn_fp16(x); the
+// product a*w is accumulated as
+//     h16(a) * h16(w)                                   one kind::f16 MMA (K = 16) into accumulator 0
+//   + [h8(a) | l8(a)] . [l8(w) | h8(w)] * 2^-17         one kind::f8f6f4 MMA (K = 32) into accumulator 1
+// where h8 = e4m3(h16), l8 = e4m3(lo * 2^11) for activations and h8 = e4m3(h16 * 2^6),
+// l8 = e4m3(lo * 2^17) for weights: the 128-byte shared-memory row of the fp8 tile holds the 64 h8
+// bytes of a k-block followed by its 64 l8 bytes (weights: l8 then h8), so ONE pass over that row
+// evaluates both cross terms lo*hi + hi*lo.  fp8 MMAs run at twice the bf16 rate: 2 tensor-time units
+// per product instead of 3.  Instruction-descriptor format fields are 0 for both F16 and E4M3.
+constexpr float F8_ACT_LO_SCALE = 2048.f;        // 2^11
+constexpr float F8_W_HI_SCALE = 64.f;            // 2^6
+constexpr float F8_W_LO_SCALE = 131072.f;        // 2^17
+constexpr float F8_CROSS_SCALE = 1.f / 131072.f; // 2^-17 = 1 / (act_lo * w_hi) = 1 / (act_hi * w_lo)
+__host__ __device__ constexpr uint32_t umma_idesc_fmt0(int n, int m) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 4 floats -> 4 packed e4m3 bytes (round to nearest even, saturate to +-448)
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  unsigned short lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %2, %1;" : "=h"(lo) : "f"(a), "f"(b));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %2, %1;" : "=h"(hi) : "f"(c), "f"(d));
+  return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+// 2 floats -> packed fp16 pair (low half = first) and the two residuals x - h16(x)
+__device__ __forceinline__ uint32_t split_h16x2(float a, float b, float& ra, float& rb) {
+  const __half2 h = __floats2half2_rn(a, b);
+  ra = a - __low2float(h);
+  rb = b - __high2float(h);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// 4 consecutive channels -> h16 (2 words), h8 (1 word), l8 (1 word); lo_scale / hi_scale as above
+__device__ __forceinline__ void split_f8x4(float a, float b, float c, float d, float hi_scale, float lo_scale,
+                                           uint2& h16, uint32_t& h8, uint32_t& l8) {
+  float ra, rb, rc, rd;
+  h16.x = split_h16x2(a, b, ra, rb);
+  h16.y = split_h16x2(c, d, rc, rd);
+  h8 = pack_e4m3x4((a - ra) * hi_scale, (b - rb) * hi_scale, (c - rc) * hi_scale, (d - rd) * hi_scale);
+  l8 = pack_e4m3x4(ra * lo_scale, rb * lo_scale, rc * lo_scale, rd * lo_scale);
 }
 
 // Branch-free MUFU wrappers (ex2.approx / rcp.approx: ~2^-22 relative error, no slow paths)

@@ -74,8 +74,17 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, long long 
 // offset field stays 0).  A stage then holds one (dy, k-block): A 2 x 130 rows + the B tiles of three
 // taps, and the A bytes pulled through L2 drop 2.95x.  These N = 64 convolutions at 128 x 128 were
 // bound by L2 -> SM bandwidth (~11 TB/s at 40 KB per 3.1 MFLOP issued), not by the tensor pipe.
-template <int BN, bool TWO, int MODE, bool STATS, bool STACK, bool HALO>
+//
+// F8 (GemmParams::f8, BN <= 128): fp16 + fp8 operands (common.cuh "f16f8").  The stage layout is
+// unchanged -- the "hi" tiles hold fp16 h16 values, the "lo" tiles hold the [h8 | l8] fp8 rows (weights:
+// [l8 | h8]) of the same k-block, 128 bytes per row either way -- but a K = 64 block costs 4 fp16 MMAs
+// into accumulator 0 plus 4 e4m3 MMAs (K = 32 each, over the 128-byte fp8 row) into accumulator 1
+// instead of 12 bf16 MMAs; the epilogue returns acc0 + 2^-17 acc1.  CPU emulation of the scheme on the
+// whole UNet (tools/experiments/precision_emul.py): max |err| 5.9e-5, rms 9.3e-6 against the fp32
+// reference (bf16x3: 2.0e-5 / 3.9e-6; tolerance 1e-4 + 1e-3 |ref|).
+template <int BN, bool TWO, int MODE, bool STATS, bool STACK, bool HALO, bool F8 = false>
 __device__ __forceinline__ void gemm_body(const GemmParams& p) {
+  static_assert(!F8 || (!STACK && BN <= 128), "f16f8 needs two accumulators of BN columns, double buffered");
   static_assert(!STACK || (TWO && BN <= 128), "stacked B operand needs cta_group::2 and 4*BN <= 512 TMEM columns");
   static_assert(!HALO || TWO, "halo stages are implemented for cta_group::2 only");
   extern __shared__ uint8_t smem_raw[];
@@ -90,9 +99,11 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   constexpr int A_SLOT = HALO ? GEMM_HALO_A_SLOT : A_BYTES;  // bytes reserved per A half (hi / lo)
   constexpr int GT = HALO ? 3 : 1;                            // taps per stage (B tile pairs reserved)
   constexpr int STAGE_BYTES = 2 * A_SLOT + GT * 2 * B_BYTES;
-  constexpr uint32_t IDESC = TWO ? umma_idesc_bf16_m256(BN) : umma_idesc_bf16(BN);
+  constexpr uint32_t IDESC = F8 ? umma_idesc_fmt0(BN, TWO ? 256 : 128)
+                                : TWO ? umma_idesc_bf16_m256(BN) : umma_idesc_bf16(BN);
   constexpr uint32_t IDESC_2N = umma_idesc_bf16_m256(STACK ? 2 * BN : BN);
-  constexpr int ACC_COLS = STACK ? 2 * BN : BN;  // TMEM columns of one accumulator stage
+  constexpr int ACC_COLS = (STACK || F8) ? 2 * BN : BN;  // TMEM columns of one accumulator stage
+  constexpr int LOMUL = F8 ? 2 : 1;  // the fp8 tensors are byte maps: 2 bytes per (channel) element
   constexpr int TMEM_COLS = 2 * ACC_COLS;        // 128 / 256 / 512: power of two >= 32
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0);
@@ -176,21 +187,21 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 // both CTAs' loads complete on the LEADER's barrier, which expects both halves
                 if (leader) mbar_expect_tx(fb, 2 * tx);
                 tma2_load_4d(sa, &sg.a_hi, fb, acol + kb * GEMM_BK, ax, ay, ai);
-                tma2_load_4d(sa + A_SLOT, &sg.a_lo, fb, acol + kb * GEMM_BK, ax, ay, ai);
+                tma2_load_4d(sa + A_SLOT, &sg.a_lo, fb, (acol + kb * GEMM_BK) * LOMUL, ax, ay, ai);
 #pragma unroll
                 for (int j = 0; j < GT; ++j) {
                   if (j < gtaps) {
                     const uint32_t sb = sa + 2 * A_SLOT + j * 2 * B_BYTES;
                     tma2_load_2d(sb, &sg.b_hi, fb, bcol + kb * GEMM_BK, br + j * sg.b_tap_stride);
-                    tma2_load_2d(sb + B_BYTES, &sg.b_lo, fb, bcol + kb * GEMM_BK, br + j * sg.b_tap_stride);
+                    tma2_load_2d(sb + B_BYTES, &sg.b_lo, fb, (bcol + kb * GEMM_BK) * LOMUL, br + j * sg.b_tap_stride);
                   }
                 }
               } else {
                 mbar_expect_tx(fb, tx);
                 tma_load_4d(sa, &sg.a_hi, fb, acol + kb * GEMM_BK, ax, ay, ai);
-                tma_load_4d(sa + A_BYTES, &sg.a_lo, fb, acol + kb * GEMM_BK, ax, ay, ai);
+                tma_load_4d(sa + A_BYTES, &sg.a_lo, fb, (acol + kb * GEMM_BK) * LOMUL, ax, ay, ai);
                 tma_load_2d(sa + 2 * A_BYTES, &sg.b_hi, fb, bcol + kb * GEMM_BK, br);
-                tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &sg.b_lo, fb, bcol + kb * GEMM_BK, br);
+                tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &sg.b_lo, fb, (bcol + kb * GEMM_BK) * LOMUL, br);
               }
             }
           }
@@ -231,7 +242,16 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 for (int k = 0; k < GEMM_BK / 16; ++k) {
                   const uint64_t ko = static_cast<uint64_t>(k * 2);  // 32 B per K=16 step (16 B units)
                   const uint32_t accum = (kbi | j | k) != 0;
-                  if (STACK) {
+                  if (F8) {
+                    // fp16 x fp16 (K = 16) and e4m3 x e4m3 (K = 32): 32 bytes of the row each
+                    if (TWO) {
+                      umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC, accum);
+                      umma2_f8(acc + BN, da_lo + ko, db_lo + ko, IDESC, accum);
+                    } else {
+                      umma_bf16(acc, da_hi + ko, db_hi + ko, IDESC, accum);
+                      umma_f8(acc + BN, da_lo + ko, db_lo + ko, IDESC, accum);
+                    }
+                  } else if (STACK) {
                     umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC_2N, accum);
                     umma2_bf16(acc + BN / 2, da_lo + ko, db_hi + ko, IDESC, 1u);
                   } else if (TWO) {
@@ -278,7 +298,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
       const long long m0 = static_cast<long long>(tc.tile) * GEMM_BM + q * 32;  // first row of this warp
       const long long zoff = tc.zb * p.out_zb + tc.zh * p.out_zh;
-      if ((MODE == OUT_F32 || MODE == OUT_SPLIT) && p.resid != nullptr) {
+      if ((MODE == OUT_F32 || MODE == OUT_SPLIT || MODE == OUT_SPLIT8) && p.resid != nullptr) {
         // Pull this warp's share of the residual into L2 one tile AHEAD (the residual was written
         // several kernels ago and has usually left L2; a DRAM round trip per chunk would otherwise
         // dominate the epilogue of the small-K GEMMs): one 128-byte line per (row, 32-col chunk).
@@ -307,7 +327,15 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * ACC_COLS);
       // logical accumulator columns [c, c + 32) of this warp's 32 rows (wait included)
       auto ld_acc = [&](int c, uint32_t (&v)[32]) {
-        if constexpr (STACK) {
+        if constexpr (F8) {
+          uint32_t w[32];
+          tmem_ld32(taddr + c, v);
+          tmem_ld32(taddr + BN + c, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = __float_as_uint(fmaf(__uint_as_float(w[j]), F8_CROSS_SCALE, __uint_as_float(v[j])));
+        } else if constexpr (STACK) {
           constexpr int h = BN / 2;
           const int ca = (c / h) * BN + (c % h);
           uint32_t w[32];
@@ -344,7 +372,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         const int ncols = geglu ? BN / 2 : BN;          // output columns produced by this tile
         const int ocol0 = geglu ? (tc.n0 / 2) : tc.n0;  // first output column
         const float* av = p.addvec ? p.addvec + static_cast<long long>(tc.img) * p.addvec_ld : nullptr;
-        const bool has_res = (MODE == OUT_F32 || MODE == OUT_SPLIT) && p.resid != nullptr;
+        const bool has_res = (MODE == OUT_F32 || MODE == OUT_SPLIT || MODE == OUT_SPLIT8) && p.resid != nullptr;
         float4 csum[STATS ? BN / 64 : 1], csq[STATS ? BN / 64 : 1];  // per-chunk column partial sums
 #pragma unroll(STATS ? BN / 64 : 1)
         for (int ci = 0; ci < BN / 64; ++ci) {
@@ -420,6 +448,20 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y);
                 ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
               }
+            } else if constexpr (MODE == OUT_SPLIT8) {
+              // f16f8 activation operand: h16 [m, ldc] fp16 + fp8 rows [m][ldc / 64][h8 x 64 | l8 x 64]
+              if (has_res) {
+                o.x += rres[it].x; o.y += rres[it].y; o.z += rres[it].z; o.w += rres[it].w;
+              }
+              uint2 h16;
+              uint32_t h8, l8;
+              split_f8x4(o.x, o.y, o.z, o.w, 1.f, F8_ACT_LO_SCALE, h16, h8, l8);
+              const int col = ocol0 + c + c4;
+              const long long row = zoff + m * p.ldc;
+              *reinterpret_cast<uint2*>(p.out_hi + row + col) = h16;
+              uint8_t* b8 = reinterpret_cast<uint8_t*>(p.out_lo) + row * 2 + (col >> 6) * 128 + (col & 63);
+              *reinterpret_cast<uint32_t*>(b8) = h8;
+              *reinterpret_cast<uint32_t*>(b8 + 64) = l8;
             } else {  // OUT_SPLIT (+ residual) / OUT_GEGLU: split-bf16 row-major
               if constexpr (MODE == OUT_SPLIT) {
                 if (has_res) {
@@ -524,6 +566,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
   gemm_body<BN, true, OUT_F32, STATS, true, true>(p);
 }
 
+// f16f8 operands (fp16 main product + e4m3 cross terms): cta_group::2, halo and single-CTA forms
+template <int BN, int MODE, bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
+    gemm_tc2f_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, true, MODE, STATS, false, false, true>(p);
+}
+template <int BN, bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
+    gemm_tc2fh_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, true, OUT_F32, STATS, false, true, true>(p);
+}
+template <int BN, int MODE, bool STATS>
+__global__ void __launch_bounds__(GEMM_LB_THREADS, 1) gemm_tcf_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, false, MODE, STATS, false, false, true>(p);
+}
+
 typedef void (*GemmKernel)(GemmParams);
 
 // variant index: 0 = fp32, 1 = fp32 + GroupNorm statistics, 2 = split, 3 = split transposed, 4 = GeGLU
@@ -536,6 +594,7 @@ static GemmKernel pick_variant(int v) {
       case 1: return gemm_tc2s_kernel<BN, OUT_F32, true>;
       case 2: return gemm_tc2s_kernel<BN, OUT_SPLIT, false>;
       case 3: return gemm_tc2s_kernel<BN, OUT_SPLIT_T, false>;
+      case 5: return gemm_tc2s_kernel<BN, OUT_SPLIT8, false>;
       default: return gemm_tc2s_kernel<BN, OUT_GEGLU, false>;
     }
   } else if constexpr (KIND == 1) {
@@ -544,6 +603,7 @@ static GemmKernel pick_variant(int v) {
       case 1: return gemm_tc2_kernel<BN, OUT_F32, true>;
       case 2: return gemm_tc2_kernel<BN, OUT_SPLIT, false>;
       case 3: return gemm_tc2_kernel<BN, OUT_SPLIT_T, false>;
+      case 5: return gemm_tc2_kernel<BN, OUT_SPLIT8, false>;
       default: return gemm_tc2_kernel<BN, OUT_GEGLU, false>;
     }
   } else {
@@ -552,12 +612,40 @@ static GemmKernel pick_variant(int v) {
       case 1: return gemm_tc_kernel<BN, OUT_F32, true>;
       case 2: return gemm_tc_kernel<BN, OUT_SPLIT, false>;
       case 3: return gemm_tc_kernel<BN, OUT_SPLIT_T, false>;
+      case 5: return gemm_tc_kernel<BN, OUT_SPLIT8, false>;
       default: return gemm_tc_kernel<BN, OUT_GEGLU, false>;
     }
   }
 }
 
+// f16f8 kernels: kind 4 = cta_group::2, 5 = cta_group::2 + halo stages, 6 = one CTA per tile;
+// variants 0 = fp32, 1 = fp32 + statistics, 2 = split-bf16 output, 5 = f16f8 split output
+template <int BN>
+static GemmKernel pick_f8(int kind, int v) {
+  if (kind == 5) {
+    if constexpr (BN == 64) return v == 1 ? gemm_tc2fh_kernel<64, true> : v == 0 ? gemm_tc2fh_kernel<64, false> : nullptr;
+    else return nullptr;
+  }
+  if (kind == 4) {
+    switch (v) {
+      case 0: return gemm_tc2f_kernel<BN, OUT_F32, false>;
+      case 1: return gemm_tc2f_kernel<BN, OUT_F32, true>;
+      case 2: return gemm_tc2f_kernel<BN, OUT_SPLIT, false>;
+      case 5: return gemm_tc2f_kernel<BN, OUT_SPLIT8, false>;
+      default: return nullptr;
+    }
+  }
+  switch (v) {
+    case 0: return gemm_tcf_kernel<BN, OUT_F32, false>;
+    case 1: return gemm_tcf_kernel<BN, OUT_F32, true>;
+    case 2: return gemm_tcf_kernel<BN, OUT_SPLIT, false>;
+    case 5: return gemm_tcf_kernel<BN, OUT_SPLIT8, false>;
+    default: return nullptr;
+  }
+}
+
 static GemmKernel pick_kernel(int bn, int kind, int v) {
+  if (kind >= 4) return bn == 64 ? pick_f8<64>(kind, v) : bn == 128 ? pick_f8<128>(kind, v) : nullptr;
   if (kind == 3) {  // halo stages: BN = 64, fp32 output (with / without statistics)
     if (bn != 64 || v > 1) return nullptr;
     return v == 1 ? gemm_tc2h_kernel<64, true> : gemm_tc2h_kernel<64, false>;
@@ -572,8 +660,8 @@ static GemmKernel pick_kernel(int bn, int kind, int v) {
 
 cudaError_t gemm_init_attrs() {
   for (int bn : {64, 128, 256})
-    for (int kind = 0; kind < 4; ++kind)
-      for (int v = 0; v < 5; ++v) {
+    for (int kind = 0; kind < 7; ++kind)
+      for (int v = 0; v < 6; ++v) {
         GemmKernel k = pick_kernel(bn, kind, v);
         if (!k) continue;
         cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k),
@@ -589,9 +677,11 @@ cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t 
     case OUT_F32: v = p.stats ? 1 : 0; break;
     case OUT_SPLIT: v = 2; break;
     case OUT_SPLIT_T: v = 3; break;
+    case OUT_SPLIT8: v = 5; break;
     default: v = 4; break;
   }
-  const int kind = p.two_cta ? (p.halo ? 3 : (p.stack && bn <= 128) ? 2 : 1) : 0;
+  const int kind = p.f8 ? (p.two_cta ? (p.halo ? 5 : 4) : 6)
+                        : p.two_cta ? (p.halo ? 3 : (p.stack && bn <= 128) ? 2 : 1) : 0;
   GemmKernel k = pick_kernel(bn, kind, v);
   if (!k) return cudaErrorInvalidValue;
   if (p.two_cta) {

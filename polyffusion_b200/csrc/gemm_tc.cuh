@@ -29,6 +29,8 @@ enum GemmOutMode : int {
   OUT_SPLIT = 1,      // bf16 hi/lo row-major [m, ldc] of (acc + addvec[img, n] + resid[m, n])
   OUT_SPLIT_T = 2,    // bf16 hi/lo transposed per image: [img][n][token]
   OUT_GEGLU = 3,      // tile = [BN/2 value cols | BN/2 gate cols]: split-bf16 of (x+b)*gelu(g+b)
+  OUT_SPLIT8 = 4,     // f16f8 activation operand of (acc + addvec + resid): out_hi = fp16 [m, ldc],
+                      // out_lo = fp8 rows [m][ldc / 64][h8 x 64 | l8 x 64] (common.cuh)
 };
 
 struct alignas(64) GemmSeg {
@@ -69,6 +71,7 @@ struct alignas(64) GemmParams {
   int two_cta;          // 1: cta_group::2 kernel (tile pairs; B maps have boxes of BN/2 rows)
   int stack;            // 1 (with two_cta, BN <= 128): stacked [B_hi ; B_lo] operand, 2 MMAs per K step
   int halo;             // 1 (with two_cta, BN = 64, box 128 x 1, OUT_F32): halo stages, see gemm_tc.cu
+  int f8;               // 1: f16f8 operands (a_hi/b_hi = fp16 maps, a_lo/b_lo = byte maps of the fp8 rows)
   // nearest-2x-upsample + conv3x3 evaluated as four 2x2 parity convolutions at LOW resolution:
   // OUT_F32 rows are scattered to pixel (2y + up_py, 2x + up_px) of the [img][2H][2W] output
   int up_mode, up_py, up_px;

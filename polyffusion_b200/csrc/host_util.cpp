@@ -56,6 +56,36 @@ CUtensorMap make_map_2d(const void* ptr, long long K, long long rows, int box_ro
   return m;
 }
 
+CUtensorMap make_map_4d_u8(const void* ptr, int C, int W, int H, int N, int box_w, int box_h) {
+  CUtensorMap m;
+  const cuuint64_t rb = (cuuint64_t)C * 2;  // bytes per pixel
+  cuuint64_t dims[4] = {rb, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {rb, (cuuint64_t)W * rb, (cuuint64_t)H * W * rb};
+  cuuint32_t box[4] = {128, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(ptr), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fail("cuTensorMapEncodeTiled(4d u8 C=%d W=%d H=%d N=%d box=%dx%d) failed: %d", C, W, H, N, box_w,
+         box_h, (int)r);
+  return m;
+}
+
+CUtensorMap make_map_2d_u8(const void* ptr, long long K, long long rows, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)K * 2, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fail("cuTensorMapEncodeTiled(2d u8 K=%lld rows=%lld box=%d) failed: %d", K, rows, box_rows, (int)r);
+  return m;
+}
+
 // ------------------------------------------------------------------ arena
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

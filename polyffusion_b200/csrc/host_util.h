@@ -47,6 +47,10 @@ struct Error : std::runtime_error {
 CUtensorMap make_map_4d(const void* ptr, int C, int W, int H, int N, int box_w, int box_h);
 // B operand: bf16 K-major matrix {K, rows}, box {64, box_rows}, 128B swizzle.
 CUtensorMap make_map_2d(const void* ptr, long long K, long long rows, int box_rows);
+// f16f8 fp8 rows (common.cuh): byte tensors with 2 bytes per channel element, {2C, W, H, N} /
+// {2K, rows}, boxes of 128 bytes (= one 64-channel k-block: 64 x h8 + 64 x l8), 128B swizzle
+CUtensorMap make_map_4d_u8(const void* ptr, int C, int W, int H, int N, int box_w, int box_h);
+CUtensorMap make_map_2d_u8(const void* ptr, long long K, long long rows, int box_rows);
 
 // ------------------------------------------------------------------ plan-time arena
 // First-fit free-list allocator over a caller-provided workspace.  Used only while a plan is being

@@ -244,6 +244,22 @@ __device__ __forceinline__ void store_split16(const float* v, bf16* oh, bf16* ol
   reinterpret_cast<uint4*>(ol)[1] = l1;
 }
 
+// f16f8 operand (common.cuh): 16 channels starting at channel c of the pixel whose row starts at
+// element offset `row` (= pixel * C): h16 [pixel][C] fp16, fp8 rows [pixel][C / 64][h8 x 64 | l8 x 64]
+__device__ __forceinline__ void store_f8_16(const float* v, bf16* o16, bf16* o8, long long row, int c) {
+  uint2 h[4];
+  uint32_t h8[4], l8[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    split_f8x4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], 1.f, F8_ACT_LO_SCALE, h[i], h8[i], l8[i]);
+  uint4* p16 = reinterpret_cast<uint4*>(o16 + row + c);
+  p16[0] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+  p16[1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+  uint8_t* p8 = reinterpret_cast<uint8_t*>(o8) + row * 2 + (c >> 6) * 128 + (c & 63);
+  *reinterpret_cast<uint4*>(p8) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+  *reinterpret_cast<uint4*>(p8 + 64) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+}
+
 __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
   pdl_wait();
   pdl_trigger();
@@ -294,7 +310,10 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
         v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
       }
     }
-    if (a.out2_hi) store_split16(v, a.out2_hi + pix * C + c, a.out2_lo + pix * C + c);
+    if (a.out2_hi) {
+      if (a.fmt8) store_f8_16(v, a.out2_hi, a.out2_lo, pix * C, c);
+      else store_split16(v, a.out2_hi + pix * C + c, a.out2_lo + pix * C + c);
+    }
     if (norm) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], s_scale[c + i], s_shift[c + i]);
@@ -304,7 +323,8 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
       for (int i = 0; i < 16; ++i) v[i] = silu_fast(v[i]);
     }
     if (a.layout == XF_SAME) {
-      store_split16(v, a.out_hi + pix * C + c, a.out_lo + pix * C + c);
+      if (a.fmt8) store_f8_16(v, a.out_hi, a.out_lo, pix * C, c);
+      else store_split16(v, a.out_hi + pix * C + c, a.out_lo + pix * C + c);
     } else {
       const int y = pl / a.W, x = pl % a.W;
       if (a.layout == XF_UP2) {
@@ -313,14 +333,16 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
           for (int dx = 0; dx < 2; ++dx) {
-            const long long o = ((static_cast<long long>(b) * H2 + 2 * y + dy) * W2 + 2 * x + dx) * C + c;
-            store_split16(v, a.out_hi + o, a.out_lo + o);
+            const long long o = ((static_cast<long long>(b) * H2 + 2 * y + dy) * W2 + 2 * x + dx) * C;
+            if (a.fmt8) store_f8_16(v, a.out_hi, a.out_lo, o, c);
+            else store_split16(v, a.out_hi + o + c, a.out_lo + o + c);
           }
       } else {  // XF_S2D: [b*4 + (y&1)*2 + (x&1)][H/2][W/2][C]
         const int Hh = a.H >> 1, Wh = a.W >> 1;
         const long long o =
-            (((static_cast<long long>(b) * 4 + (y & 1) * 2 + (x & 1)) * Hh + (y >> 1)) * Wh + (x >> 1)) * C + c;
-        store_split16(v, a.out_hi + o, a.out_lo + o);
+            (((static_cast<long long>(b) * 4 + (y & 1) * 2 + (x & 1)) * Hh + (y >> 1)) * Wh + (x >> 1)) * C;
+        if (a.fmt8) store_f8_16(v, a.out_hi, a.out_lo, o, c);
+        else store_split16(v, a.out_hi + o + c, a.out_lo + o + c);
       }
     }
   }
@@ -519,6 +541,135 @@ void launch_time_sinusoid(const long long* t, const float* freqs, float* out, in
 }
 
 // test helpers: fp32 = hi + lo, and [rows, C] -> transposed split [C, rows] per image
+// ------------------------------------------------------------------------------------------------
+// Generic building blocks of the legacy ddpm.unet.UNet evaluation (polyffusion_b200/ddpm/unet.py):
+// any channel count / group count GroupNorm (+ Swish), row softmax, sin-then-cos timestep embedding.
+// Not on the sdf sampling path (those shapes use the fused kernels above).
+// ------------------------------------------------------------------------------------------------
+// one block per (sample, group): two passes over the group's [HW, cpg] elements (fp64 accumulation)
+__global__ void __launch_bounds__(256) groupnorm_generic_kernel(const float* __restrict__ x,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps,
+                                                                int silu, float* __restrict__ out, int HW,
+                                                                int C, int groups) {
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cpg = C / groups;
+  const float* xb = x + static_cast<long long>(b) * HW * C + g * cpg;
+  float* ob = out + static_cast<long long>(b) * HW * C + g * cpg;
+  const int n = HW * cpg;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float v = xb[static_cast<long long>(i / cpg) * C + i % cpg];
+    s1 += v;
+    s2 += static_cast<double>(v) * v;
+  }
+  __shared__ double r1[256], r2[256];
+  r1[threadIdx.x] = s1;
+  r2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      r1[threadIdx.x] += r1[threadIdx.x + o];
+      r2[threadIdx.x] += r2[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const double mean = r1[0] / n;
+  double var = r2[0] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float mu = static_cast<float>(mean);
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int c = i % cpg;
+    const long long o = static_cast<long long>(i / cpg) * C + c;
+    float v = (xb[o] - mu) * rstd * gamma[g * cpg + c] + beta[g * cpg + c];
+    if (silu) v = v / (1.0f + expf(-v));
+    ob[o] = v;
+  }
+}
+void launch_groupnorm_generic(const float* x, const float* gamma, const float* beta, float eps, int silu,
+                              float* out, int B, int HW, int C, int groups, cudaStream_t s) {
+  groupnorm_generic_kernel<<<B * groups, 256, 0, s>>>(x, gamma, beta, eps, silu, out, HW, C, groups);
+}
+
+// out[r, :] = softmax(scale * S[r, :]); one warp per row, any n
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, float scale,
+                                                           float* __restrict__ out, long long rows, int n) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* sp = S + row * n;
+  float mx = -INFINITY;
+  for (int i = lane; i < n; i += 32) mx = fmaxf(mx, sp[i] * scale);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < n; i += 32) sum += expf(sp[i] * scale - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int i = lane; i < n; i += 32) out[row * n + i] = expf(sp[i] * scale - mx) * inv;
+}
+void launch_softmax_rows(const float* S, float scale, float* out, long long rows, int n, cudaStream_t s) {
+  softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(S, scale, out, rows, n);
+}
+
+// direct fp32 3x3 convolution (pad 1) for the two edge layers whose channel count is not GEMM-shaped
+// (image_proj 2 -> 64 from NCHW, final 64 -> 2 to NCHW; ddpm/unet.py:345-347, 405-407): one thread per
+// output element, taps in the order ky, kx, ci of a [Cout][Cin][3][3] weight
+__global__ void __launch_bounds__(256) conv3x3_direct_kernel(const float* __restrict__ x,
+                                                             const float* __restrict__ w,
+                                                             const float* __restrict__ bias,
+                                                             float* __restrict__ out, int B, int Cin, int H,
+                                                             int W, int Cout, int in_nchw, int out_nchw) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H * W * Cout;
+  if (i >= total) return;
+  int b, co, y, xx;
+  if (out_nchw) {
+    xx = static_cast<int>(i % W); y = static_cast<int>((i / W) % H);
+    co = static_cast<int>((i / (static_cast<long long>(W) * H)) % Cout);
+    b = static_cast<int>(i / (static_cast<long long>(W) * H * Cout));
+  } else {
+    co = static_cast<int>(i % Cout); xx = static_cast<int>((i / Cout) % W);
+    y = static_cast<int>((i / (static_cast<long long>(Cout) * W)) % H);
+    b = static_cast<int>(i / (static_cast<long long>(Cout) * W * H));
+  }
+  float acc = bias ? bias[co] : 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = y + ky - 1;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = xx + kx - 1;
+      if (ix < 0 || ix >= W) continue;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float v = in_nchw ? x[((static_cast<long long>(b) * Cin + ci) * H + iy) * W + ix]
+                                : x[((static_cast<long long>(b) * H + iy) * W + ix) * Cin + ci];
+        acc = fmaf(v, w[((static_cast<long long>(co) * Cin + ci) * 3 + ky) * 3 + kx], acc);
+      }
+    }
+  }
+  out[i] = acc;
+}
+void launch_conv3x3_direct(const float* x, const float* w, const float* bias, float* out, int B, int Cin,
+                           int H, int W, int Cout, int in_nchw, int out_nchw, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * H * W * Cout;
+  conv3x3_direct_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x, w, bias, out, B, Cin, H, W,
+                                                                                    Cout, in_nchw, out_nchw);
+}
+
+// legacy TimeEmbedding (ddpm/unet.py:62-72): [sin(t f_i), cos(t f_i)], t converted to fp32 first
+__global__ void time_sincos_kernel(const long long* __restrict__ t, const float* __restrict__ freqs,
+                                   float* __restrict__ out, int B, int half) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i % half;
+  const float a = static_cast<float>(t[b]) * freqs[k];
+  out[b * 2 * half + k] = sinf(a);
+  out[b * 2 * half + half + k] = cosf(a);
+}
+void launch_time_sincos(const long long* t, const float* freqs, float* out, int B, int half, cudaStream_t s) {
+  time_sincos_kernel<<<(B * half + 127) / 128, 128, 0, s>>>(t, freqs, out, B, half);
+}
+
 __global__ void merge_split_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo,
                                    float* __restrict__ out, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
@@ -1010,9 +1161,22 @@ void launch_prmat_notes(const long long* dur, int* offsets, int* notes, long lon
 // ------------------------------------------------------------------------------------------------
 // weight packing / misc
 // ------------------------------------------------------------------------------------------------
+// f16f8 weight element (common.cuh): h16 at element o of the fp16 tensor; fp8 row bytes
+// [row][Cin / 64][l8 x 64 | h8 x 64] (the ACTIVATION rows are [h8 | l8], so one K pass pairs
+// act.h8 with w.l8 and act.l8 with w.h8)
+__device__ __forceinline__ void store_weight_f8(float v, bf16* o16, bf16* o8, long long rowoff, int ci) {
+  const __half h = __float2half_rn(v);
+  const float hf = __half2float(h);
+  reinterpret_cast<__half*>(o16)[rowoff + ci] = h;
+  const uint32_t q = pack_e4m3x4(hf * F8_W_HI_SCALE, (v - hf) * F8_W_LO_SCALE, 0.f, 0.f);
+  uint8_t* p8 = reinterpret_cast<uint8_t*>(o8) + rowoff * 2 + (ci >> 6) * 128 + (ci & 63);
+  p8[0] = static_cast<uint8_t>((q >> 8) & 0xffu);   // l8
+  p8[64] = static_cast<uint8_t>(q & 0xffu);         // h8
+}
+
 __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out_hi,
                                    bf16* __restrict__ out_lo, int Cout, int Cin, int taps,
-                                   int cout_total, int row0, int geglu_gran) {
+                                   int cout_total, int row0, int geglu_gran, int fmt8) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   if (i >= total) return;
@@ -1031,21 +1195,25 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
     dst = row0 + (r / geglu_gran) * 2 * geglu_gran + half * geglu_gran + r % geglu_gran;
   }
   const long long o = (static_cast<long long>(tap) * cout_total + dst) * Cin + ci;
+  if (fmt8) {
+    store_weight_f8(v, out_hi, out_lo, o - ci, ci);
+    return;
+  }
   out_hi[o] = h;
   out_lo[o] = l;
 }
 void launch_pack_weight(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin, int taps,
-                        int cout_total, int row0, int geglu_gran, cudaStream_t s) {
+                        int cout_total, int row0, int geglu_gran, cudaStream_t s, int fmt8) {
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   pack_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
-      w, out_hi, out_lo, Cout, Cin, taps, cout_total, row0, geglu_gran);
+      w, out_hi, out_lo, Cout, Cin, taps, cout_total, row0, geglu_gran, fmt8);
 }
 
 // UpSample conv (nearest 2x then 3x3, unet.py:231-238) as four 2x2 parity kernels over the
 // low-resolution input: for output parity (py, px) and tap (a, b) the effective weight is the sum of
 // the 3x3 taps that read the same source pixel.  out: [parity 4][tap 4][Cout][Cin] split bf16.
 __global__ void pack_weight_up_kernel(const float* __restrict__ w, bf16* __restrict__ out_hi,
-                                      bf16* __restrict__ out_lo, int Cout, int Cin) {
+                                      bf16* __restrict__ out_lo, int Cout, int Cin, int fmt8) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long per = static_cast<long long>(Cout) * Cin;
   if (i >= 16 * per) return;
@@ -1063,16 +1231,20 @@ __global__ void pack_weight_up_kernel(const float* __restrict__ w, bf16* __restr
   float v = 0.f;
   for (int ky = ky0; ky <= ky1; ++ky)
     for (int kx = kx0; kx <= kx1; ++kx) v += wp[ky * 3 + kx];
+  if (fmt8) {
+    store_weight_f8(v, out_hi, out_lo, i - ci, ci);
+    return;
+  }
   bf16 h, l;
   split_bf16(v, h, l);
   out_hi[i] = h;
   out_lo[i] = l;
 }
 void launch_pack_weight_up(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin,
-                           cudaStream_t s) {
+                           cudaStream_t s, int fmt8) {
   const long long total = 16LL * Cout * Cin;
   pack_weight_up_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, out_hi, out_lo,
-                                                                                   Cout, Cin);
+                                                                                   Cout, Cin, fmt8);
 }
 
 // ------------------------------------------------------------------------------------------------

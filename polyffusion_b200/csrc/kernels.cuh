@@ -38,6 +38,7 @@ struct ActSplitArgs {
   bf16* out_hi; bf16* out_lo;
   bf16* out2_hi; bf16* out2_lo;
   int B, H, W;
+  int fmt8;  // 1: outputs are f16f8 operands (out_hi = fp16 [pixel][C], out_lo = fp8 rows), see common.cuh
 };
 void launch_act_split(const ActSplitArgs& a, cudaStream_t s);
 
@@ -54,6 +55,13 @@ void launch_softmax_split(const float* S, float scale, bf16* out_hi, bf16* out_l
 // sinusoidal timestep embedding [B, 2*half] = [cos(t f_i), sin(t f_i)] (unet.py:151-169)
 void launch_time_sinusoid(const long long* t, const float* freqs, float* out, int B, int half,
                           cudaStream_t s);
+// generic blocks of the legacy ddpm.unet.UNet evaluation (kernels.cu)
+void launch_groupnorm_generic(const float* x, const float* gamma, const float* beta, float eps, int silu,
+                              float* out, int B, int HW, int C, int groups, cudaStream_t s);
+void launch_softmax_rows(const float* S, float scale, float* out, long long rows, int n, cudaStream_t s);
+void launch_conv3x3_direct(const float* x, const float* w, const float* bias, float* out, int B, int Cin,
+                           int H, int W, int Cout, int in_nchw, int out_nchw, cudaStream_t s);
+void launch_time_sincos(const long long* t, const float* freqs, float* out, int B, int half, cudaStream_t s);
 // test helpers
 void launch_merge_split(const bf16* hi, const bf16* lo, float* out, long long n, cudaStream_t s);
 void launch_transpose_split(const float* src, bf16* hi, bf16* lo, int imgs, int rows, int C,
@@ -84,10 +92,10 @@ void launch_prmat_notes(const long long* dur, int* offsets, int* notes, long lon
 // weight packing: w [Cout, Cin, kh, kw] fp32 -> split bf16 [kh*kw][Cout_total][Cin] rows at row0
 // geglu_gran > 0: interleave the [x | gate] halves of a GeGLU projection in blocks of geglu_gran rows
 void launch_pack_weight(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin, int taps,
-                        int cout_total, int row0, int geglu_gran, cudaStream_t s);
+                        int cout_total, int row0, int geglu_gran, cudaStream_t s, int fmt8 = 0);
 // UpSample conv weights w [Cout, Cin, 3, 3] -> four 2x2 parity kernels [parity 4][tap 4][Cout][Cin]
 void launch_pack_weight_up(const float* w, bf16* out_hi, bf16* out_lo, int Cout, int Cin,
-                           cudaStream_t s);
+                           cudaStream_t s, int fmt8 = 0);
 // get_mask("below"/"above") of inference_sdf.py:132-180, batched over songs (see kernels.cu).
 // rowval: scratch [n_seg * T] ints; err: device int set to 1 if a song has no onset at all.
 int launch_get_mask(const float* orig, float* mask, int* rowval, int* err, int n_seg, int seg_per_song,

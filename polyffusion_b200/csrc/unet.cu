@@ -39,8 +39,23 @@ struct PackedW {
   int rows = 0;  // Cout total per tap
   int K = 0;     // Cin
   int taps = 1;
+  bool f8 = false;  // f16f8 format: hi = fp16 [tap][row][K], lo = fp8 rows [tap][row][K/64][l8 x 64 | h8 x 64]
   std::map<int, std::pair<CUtensorMap, CUtensorMap>> maps;  // by box rows (BN)
 };
+
+// Convolutions (3x3, 1x1 skip, up / down sampling) run on fp16 + fp8 operands: 2 tensor-time units per
+// product instead of 3 (common.cuh).  Measured on B200, batch 64 (profiles/r3c_*): 18.3 ms per DDPM step
+// against 19.9 ms with split-bf16 everywhere; UNet max |err| against the reference goldens 4.7e-5
+// (split-bf16: 2.0e-5; tolerance 1e-4 + 1e-3 |ref|, worst element at 0.34 of its bound).
+// PF_CONV_F8_MAX_HW=<pixels> restricts the scheme to convolutions whose input and output maps have at
+// most that many pixels: 4096 keeps split-bf16 at the 128 x 128 level, which sits next to the network's
+// input and output and carries most of the operand-rounding error (3.3e-5, 18.7 ms); 0 selects
+// split-bf16 everywhere.  The transformer linears and the attention kernel always use split-bf16.
+static bool conv_f8(long long hw_in, long long hw_out) {
+  static const long long max_hw =
+      std::getenv("PF_CONV_F8_MAX_HW") ? std::atoll(std::getenv("PF_CONV_F8_MAX_HW")) : (1ll << 40);
+  return std::max(hw_in, hw_out) <= max_hw;
+}
 
 struct ResSpec {
   std::string name;
@@ -266,8 +281,9 @@ static const float* Fcat(pf_unet* m, const std::string& key, const std::vector<s
 }
 
 // split-bf16 tap-major packed GEMM weight: concatenation of `names` along Cout
-static PackedW& W(pf_unet* m, const std::string& key, const std::vector<std::string>& names,
-                  int geglu_gran = 0) {
+static PackedW& W(pf_unet* m, const std::string& key0, const std::vector<std::string>& names,
+                  int geglu_gran = 0, bool f8 = false) {
+  const std::string key = f8 ? key0 + ":f8" : key0;
   auto it = m->packed.find(key);
   if (it != m->packed.end()) return it->second;
   PF_CHECK(m->packing, "packed weight '%s' was not prepared by pf_unet_finalize", key.c_str());
@@ -288,6 +304,7 @@ static PackedW& W(pf_unet* m, const std::string& key, const std::vector<std::str
   pw.rows = rows;
   pw.K = K;
   pw.taps = taps;
+  pw.f8 = f8;
   const size_t bytes = static_cast<size_t>(taps) * rows * K * sizeof(bf16);
   pw.hi = static_cast<bf16*>(dev_alloc(m, bytes));
   pw.lo = static_cast<bf16*>(dev_alloc(m, bytes));
@@ -295,15 +312,15 @@ static PackedW& W(pf_unet* m, const std::string& key, const std::vector<std::str
   for (auto& n : names) {
     const RawTensor& r = raw(m, n);
     launch_pack_weight(r.ptr, pw.hi, pw.lo, static_cast<int>(r.shape[0]), K, taps, rows, row0,
-                       geglu_gran, m->pack_stream);
+                       geglu_gran, m->pack_stream, f8 ? 1 : 0);
     row0 += static_cast<int>(r.shape[0]);
   }
   return m->packed[key] = pw;
 }
 
 // UpSample conv weight folded into four 2x2 parity kernels (taps = 16: [parity][tap])
-static PackedW& W_up(pf_unet* m, const std::string& name) {
-  const std::string key = name + ":up2x2";
+static PackedW& W_up(pf_unet* m, const std::string& name, bool f8 = false) {
+  const std::string key = name + (f8 ? ":up2x2:f8" : ":up2x2");
   auto it = m->packed.find(key);
   if (it != m->packed.end()) return it->second;
   PF_CHECK(m->packing, "packed weight '%s' was not prepared by pf_unet_finalize", key.c_str());
@@ -313,11 +330,12 @@ static PackedW& W_up(pf_unet* m, const std::string& name) {
   pw.rows = static_cast<int>(r.shape[0]);
   pw.K = static_cast<int>(r.shape[1]);
   pw.taps = 16;
+  pw.f8 = f8;
   PF_CHECK(pw.K % 64 == 0 && pw.rows % 64 == 0, "UpSample channels must be multiples of 64");
   const size_t bytes = static_cast<size_t>(16) * pw.rows * pw.K * sizeof(bf16);
   pw.hi = static_cast<bf16*>(dev_alloc(m, bytes));
   pw.lo = static_cast<bf16*>(dev_alloc(m, bytes));
-  launch_pack_weight_up(r.ptr, pw.hi, pw.lo, pw.rows, pw.K, m->pack_stream);
+  launch_pack_weight_up(r.ptr, pw.hi, pw.lo, pw.rows, pw.K, m->pack_stream, f8 ? 1 : 0);
   return m->packed[key] = pw;
 }
 
@@ -328,7 +346,8 @@ static const std::pair<CUtensorMap, CUtensorMap>& wmaps(PackedW& w, int bn, bool
   memset(&mp, 0, sizeof mp);
   if (!dry) {
     mp.first = make_map_2d(w.hi, w.K, static_cast<long long>(w.taps) * w.rows, bn);
-    mp.second = make_map_2d(w.lo, w.K, static_cast<long long>(w.taps) * w.rows, bn);
+    mp.second = w.f8 ? make_map_2d_u8(w.lo, w.K, static_cast<long long>(w.taps) * w.rows, bn)
+                     : make_map_2d(w.lo, w.K, static_cast<long long>(w.taps) * w.rows, bn);
     return w.maps[bn] = mp;
   }
   static std::pair<CUtensorMap, CUtensorMap> dummy;
@@ -343,6 +362,7 @@ struct T {  // fp32 NHWC activation
   // set instead of p when the only consumer wants the plain split-bf16 operand (UpSample input):
   // the producing GEMM's epilogue wrote it directly, no fp32 copy exists
   Split sp;
+  bool sp_f8 = false;  // format of sp: f16f8 (common.cuh) or split-bf16
 };
 
 // Half-batch lanes.  The high-resolution ends of the UNet (no attention, few channels) alternate an
@@ -470,7 +490,7 @@ struct Builder {
   // split-bf16 operand of act(GN(cat(x0, x1))).  norm_prefix empty -> no normalisation.  When
   // `plain` is given it receives the plain split of the same input (one pass, two outputs).
   Split act_split(const T& x0, const T* x1, const std::string& norm_prefix, float eps, bool silu,
-                  int layout, Split* plain = nullptr) {
+                  int layout, Split* plain = nullptr, bool f8 = false) {
     const int C = x0.C + (x1 ? x1->C : 0);
     PF_CHECK(C % 16 == 0 && x0.C % 16 == 0 && (norm_prefix.empty() || C <= 512),
              "operand transform: unsupported channels %d+%d", x0.C, x1 ? x1->C : 0);
@@ -500,6 +520,8 @@ struct Builder {
     a.out_hi = s.hi; a.out_lo = s.lo;
     a.out2_hi = plain ? plain->hi : nullptr; a.out2_lo = plain ? plain->lo : nullptr;
     a.B = B; a.H = x0.H; a.W = x0.W;
+    a.fmt8 = f8 ? 1 : 0;
+    PF_CHECK(!f8 || (C % 64 == 0), "f16f8 operand: channels %d not a multiple of 64", C);
     return s;
   }
 
@@ -530,6 +552,7 @@ struct Builder {
     int C;        // channels of the operand tensor (TMA dim 0)
     int W, H, N;  // TMA dims 1..3
     int kind;     // 0 = 1x1 (no shift), 1 = 3x3, 2 = 3x3 stride-2 over S2D planes
+    bool f8 = false;  // f16f8 operand (buf.hi = fp16, buf.lo = fp8 rows)
   };
 
   void fill_seg(GemmSeg& sg, const ASrc& a, PackedW& w, int b_box_rows, int box_w, int box_h,
@@ -558,9 +581,11 @@ struct Builder {
     sg.gtaps = grouped ? 3 : 1;
     sg.a_rows = grouped ? GEMM_HALO_ROWS : 128;
     if (grouped) box_w = GEMM_HALO_ROWS;
+    PF_CHECK(a.f8 == w.f8, "GEMM operand formats differ (activation f8=%d, weight f8=%d)", (int)a.f8, (int)w.f8);
     if (!dry) {
       sg.a_hi = make_map_4d(a.buf.hi, a.C, a.W, a.H, a.N, box_w, box_h);
-      sg.a_lo = make_map_4d(a.buf.lo, a.C, a.W, a.H, a.N, box_w, box_h);
+      sg.a_lo = a.f8 ? make_map_4d_u8(a.buf.lo, a.C, a.W, a.H, a.N, box_w, box_h)
+                     : make_map_4d(a.buf.lo, a.C, a.W, a.H, a.N, box_w, box_h);
       auto& mp = wmaps(w, b_box_rows, dry);
       sg.b_hi = mp.first;
       sg.b_lo = mp.second;
@@ -589,11 +614,14 @@ struct Builder {
     // stacked [B_hi ; B_lo] operand (2 MMAs per K step, fewer smem operand reads) for BN <= 128;
     // PF_GEMM_STACK = 0 (off) / 64 / 128 (only that tile width) for A/B measurements
     static const int stack_sel = std::getenv("PF_GEMM_STACK") ? std::atoi(std::getenv("PF_GEMM_STACK")) : -1;
-    g.stack = (two && bn <= 128 && (stack_sel < 0 || stack_sel == bn)) ? 1 : 0;
+    g.f8 = a0.f8 ? 1 : 0;
+    PF_CHECK(!a1 || a1->f8 == a0.f8, "GEMM segments with different operand formats");
+    PF_CHECK(!g.f8 || bn <= 128, "f16f8 GEMM: BN=%d > 128", bn);
+    g.stack = (!g.f8 && two && bn <= 128 && (stack_sel < 0 || stack_sel == bn)) ? 1 : 0;
     // halo stages for the N = 64 3x3 convolutions at 128 x 128 (tile = one image row): A bytes
     // through L2 drop 2.95x (these launches were L2 -> SM bandwidth bound).  PF_GEMM_HALO=0 disables.
     static const bool halo_ok = !(std::getenv("PF_GEMM_HALO") && std::atoi(std::getenv("PF_GEMM_HALO")) == 0);
-    const bool halo = halo_ok && f32_out && two && g.stack && bn == 64 && box_w == 128 && box_h == 1 && a0.kind == 1 &&
+    const bool halo = halo_ok && f32_out && two && (g.stack || g.f8) && bn == 64 && box_w == 128 && box_h == 1 && a0.kind == 1 &&
                       (!a1 || a1->kind == 0);
     g.halo = halo ? 1 : 0;
     fill_seg(g.seg[0], a0, w0, two ? bn / 2 : bn, box_w, box_h, halo);
@@ -629,8 +657,8 @@ struct Builder {
 
   // split-bf16 output of (acc + addvec + resid): the consumer is a GEMM that takes the value as is
   void out_split(Op& op, const Split& out, int ldc, const float* addvec, long long addvec_ld,
-                 const float* resid, long long ldr) {
-    op.g.mode = OUT_SPLIT;
+                 const float* resid, long long ldr, bool f8out = false) {
+    op.g.mode = f8out ? OUT_SPLIT8 : OUT_SPLIT;
     op.g.out_hi = out.hi;
     op.g.out_lo = out.lo;
     op.g.ldc = ldc;
@@ -647,45 +675,48 @@ struct Builder {
     PF_CHECK(C == L.cin, "ResBlock %s: got %d input channels, expected %d", L.name.c_str(), C, L.cin);
     const int H = x0.H, Wd = x0.W;
     const size_t npix = static_cast<size_t>(B) * H * Wd;
+    const bool f8 = conv_f8(static_cast<long long>(H) * Wd, static_cast<long long>(H) * Wd);
+    const bool f8_up = conv_f8(static_cast<long long>(H) * Wd, 4ll * H * Wd);  // format an UpSample consumer wants
     Split a3;  // plain split of the input for the 1x1 skip conv (same pass as the normalised one)
     Split a1 = act_split(x0, x1, L.name + ".in_layers.0", 1e-5f, true, XF_SAME,
-                         L.cin != L.cout ? &a3 : nullptr);
+                         L.cin != L.cout ? &a3 : nullptr, f8);
     T h1;
     h1.C = L.cout; h1.H = H; h1.W = Wd;
     h1.p = alloc<float>(npix * L.cout);
     {
-      PackedW& w = W(m, L.name + ".in_layers.2.weight", {L.name + ".in_layers.2.weight"});
-      ASrc a{a1, C, Wd, H, B, 1};
+      PackedW& w = W(m, L.name + ".in_layers.2.weight", {L.name + ".in_layers.2.weight"}, 0, f8);
+      ASrc a{a1, C, Wd, H, B, 1, f8};
       Op& op = conv_gemm(a, w, nullptr, nullptr, H, Wd, L.cout);
       // addvec = Linear(SiLU(t_emb)) + emb bias + conv1 bias  (unet.py:308-316)
       h1.stats = new_stats(L.cout);
       out_f32(op, h1.p, L.cout, emb_all + L.emb_off, m->emb_total, nullptr, 0, h1.stats);
     }
     free_split(a1);
-    Split a2 = act_split(h1, nullptr, L.name + ".out_layers.0", 1e-5f, true, XF_SAME);
+    Split a2 = act_split(h1, nullptr, L.name + ".out_layers.0", 1e-5f, true, XF_SAME, nullptr, f8);
     afree(h1.p);
     T y;
     y.C = L.cout; y.H = H; y.W = Wd;
+    y.sp_f8 = f8_up;
     if (split_only) y.sp = alloc_split_out(npix * L.cout);
     else {
       y.p = alloc_out<float>(npix * L.cout);
       y.stats = new_stats(L.cout);
     }
-    PackedW& w2 = W(m, L.name + ".out_layers.3.weight", {L.name + ".out_layers.3.weight"});
-    ASrc s2{a2, L.cout, Wd, H, B, 1};
+    PackedW& w2 = W(m, L.name + ".out_layers.3.weight", {L.name + ".out_layers.3.weight"}, 0, f8);
+    ASrc s2{a2, L.cout, Wd, H, B, 1, f8};
     if (L.cin != L.cout) {
-      PackedW& ws = W(m, L.name + ".skip_connection.weight", {L.name + ".skip_connection.weight"});
-      ASrc s3{a3, C, Wd, H, B, 0};
+      PackedW& ws = W(m, L.name + ".skip_connection.weight", {L.name + ".skip_connection.weight"}, 0, f8);
+      ASrc s3{a3, C, Wd, H, B, 0, f8};
       const float* bsum = Fsum(m, L.name + ".out_layers.3.bias", L.name + ".skip_connection.bias");
       Op& op = conv_gemm(s2, w2, &s3, &ws, H, Wd, L.cout, 0, 0, !split_only);
-      if (split_only) out_split(op, y.sp, L.cout, bsum, 0, nullptr, 0);
+      if (split_only) out_split(op, y.sp, L.cout, bsum, 0, nullptr, 0, f8_up);
       else out_f32(op, y.p, L.cout, bsum, 0, nullptr, 0, y.stats);
       free_split(a3);
     } else {
       PF_CHECK(!x1, "identity skip with concatenated input");
       Op& op = conv_gemm(s2, w2, nullptr, nullptr, H, Wd, L.cout, 0, 0, !split_only);
       const float* b2 = F(m, L.name + ".out_layers.3.bias");
-      if (split_only) out_split(op, y.sp, L.cout, b2, 0, x0.p, x0.C);
+      if (split_only) out_split(op, y.sp, L.cout, b2, 0, x0.p, x0.C, f8_up);
       else out_f32(op, y.p, L.cout, b2, 0, x0.p, x0.C, y.stats);
     }
     free_split(a2);
@@ -975,7 +1006,8 @@ struct Builder {
                          nullptr, H, Wd, C, 0, 0, !split_only);
       if (split_only) {
         y.sp = alloc_split_out(rows * C);
-        out_split(op, y.sp, C, F(m, L.name + ".proj_out.bias"), 0, x.p, C);
+        y.sp_f8 = conv_f8(static_cast<long long>(N), 4ll * N);  // consumed by an UpSample convolution
+        out_split(op, y.sp, C, F(m, L.name + ".proj_out.bias"), 0, x.p, C, y.sp_f8);
       } else {
         y.p = alloc_out<float>(rows * C);
         y.stats = new_stats(C);
@@ -988,12 +1020,13 @@ struct Builder {
 
   T down_sample(const Layer& L, const T& x) {
     PF_CHECK(x.H % 2 == 0 && x.W % 2 == 0, "DownSample needs even dims");
-    Split a = act_split(x, nullptr, "", 0.f, false, XF_S2D);
+    const bool f8 = conv_f8(static_cast<long long>(x.H) * x.W, static_cast<long long>(x.H) * x.W / 4);
+    Split a = act_split(x, nullptr, "", 0.f, false, XF_S2D, nullptr, f8);
     T y;
     y.C = x.C; y.H = x.H / 2; y.W = x.W / 2;
     y.p = alloc_out<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
-    ASrc s{a, x.C, y.W, y.H, 4 * B, 2};
-    Op& op = conv_gemm(s, W(m, L.name + ".op.weight", {L.name + ".op.weight"}), nullptr, nullptr, y.H,
+    ASrc s{a, x.C, y.W, y.H, 4 * B, 2, f8};
+    Op& op = conv_gemm(s, W(m, L.name + ".op.weight", {L.name + ".op.weight"}, 0, f8), nullptr, nullptr, y.H,
                        y.W, y.C);
     y.stats = new_stats(y.C);
     out_f32(op, y.p, y.C, F(m, L.name + ".op.bias"), 0, nullptr, 0, y.stats);
@@ -1004,14 +1037,16 @@ struct Builder {
   T up_sample(const Layer& L, const T& x) {
     // conv3x3(nearest2x(x)) == four 2x2 convolutions of x, one per output parity (weights folded at
     // finalize): 16 tap-GEMMs at low resolution instead of 36, and no 4x upsampled tensor.
-    Split a = x.sp.hi ? x.sp : act_split(x, nullptr, "", 0.f, false, XF_SAME);
+    const bool f8 = conv_f8(static_cast<long long>(x.H) * x.W, 4ll * x.H * x.W);
+    PF_CHECK(!x.sp.hi || x.sp_f8 == f8, "UpSample input operand has the wrong format");
+    Split a = x.sp.hi ? x.sp : act_split(x, nullptr, "", 0.f, false, XF_SAME, nullptr, f8);
     T y;
     y.C = x.C; y.H = x.H * 2; y.W = x.W * 2;
     y.p = alloc_out<float>(static_cast<size_t>(B) * y.H * y.W * y.C);
     y.stats = new_stats(y.C);
-    PackedW& w = W_up(m, L.name + ".conv.weight");
+    PackedW& w = W_up(m, L.name + ".conv.weight", f8);
     for (int par = 0; par < 4; ++par) {
-      ASrc s{a, x.C, x.W, x.H, B, 3 + par};
+      ASrc s{a, x.C, x.W, x.H, B, 3 + par, f8};
       Op& op = conv_gemm(s, w, nullptr, nullptr, x.H, x.W, y.C, par * 4 * w.rows);
       out_f32(op, y.p, y.C, F(m, L.name + ".conv.bias"), 0, nullptr, 0, y.stats);
       op.g.up_mode = 1;
@@ -1886,6 +1921,52 @@ int pf_op_conv2d_nhwc(const float* x, int32_t B, int32_t H, int32_t W_, int32_t 
                       int32_t Cout, int32_t ksize, int32_t stride, int32_t upsample,
                       const float* bias, const float* resid, float* out, int32_t force_bn,
                       pf_stream stream) {
+  return pf_op_conv2d_nhwc_ex(x, B, H, W_, Cin, w, Cout, ksize, stride, upsample, bias, 0, resid, out,
+                              force_bn, stream);
+}
+
+int pf_op_groupnorm_generic(const float* x, int32_t B, int32_t HW, int32_t C, int32_t groups,
+                            const float* gamma, const float* beta, float eps, int32_t silu, float* out,
+                            pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(x && gamma && beta && out && B > 0 && HW > 0 && groups > 0 && C % groups == 0,
+             "bad groupnorm arguments");
+    launch_groupnorm_generic(x, gamma, beta, eps, silu, out, B, HW, C, groups, static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
+int pf_op_softmax_rows(const float* s_in, float scale, float* out, int64_t rows, int32_t n, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(s_in && out && rows > 0 && n > 0, "bad softmax arguments");
+    launch_softmax_rows(s_in, scale, out, rows, n, static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
+int pf_op_conv3x3_direct(const float* x, const float* w, const float* bias, float* out, int32_t B,
+                         int32_t Cin, int32_t H, int32_t W_, int32_t Cout, int32_t in_nchw, int32_t out_nchw,
+                         pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(x && w && out && B > 0 && Cin > 0 && Cout > 0 && H > 0 && W_ > 0, "bad conv arguments");
+    launch_conv3x3_direct(x, w, bias, out, B, Cin, H, W_, Cout, in_nchw, out_nchw, static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
+int pf_op_time_sincos(const int64_t* t, const float* freqs, float* out, int32_t B, int32_t half,
+                      pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(t && freqs && out && B > 0 && half > 0, "bad time embedding arguments");
+    launch_time_sincos(reinterpret_cast<const long long*>(t), freqs, out, B, half, static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
+int pf_op_conv2d_nhwc_ex(const float* x, int32_t B, int32_t H, int32_t W_, int32_t Cin, const float* w,
+                         int32_t Cout, int32_t ksize, int32_t stride, int32_t upsample,
+                         const float* bias, int64_t bias_ld, const float* resid, float* out,
+                         int32_t force_bn, pf_stream stream) {
   return guarded([&] {
     PF_CHECK(x && w && out, "null argument");
     PF_CHECK(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
@@ -1900,25 +1981,29 @@ int pf_op_conv2d_nhwc(const float* x, int32_t B, int32_t H, int32_t W_, int32_t 
     Builder b(&tm.m, &plan, static_cast<char*>(tm.ws), false, B, 1);
     T xt;
     xt.p = const_cast<float*>(x); xt.C = Cin; xt.H = H; xt.W = W_;
+    // same operand format as the UNet plan's convolutions (BN = 256 tiles exist for split-bf16 only)
+    // (the test op ignores the resolution rule so that both schemes can be exercised at every shape)
+    static const bool op_f8 = !(std::getenv("PF_CONV_F8_MAX_HW") && std::atoll(std::getenv("PF_CONV_F8_MAX_HW")) == 0);
+    const bool f8 = op_f8 && force_bn <= 128 && Cin % 64 == 0;
     if (upsample) {
       // same path as UNetModel's UpSample layers: four 2x2 parity convolutions at low resolution
       PF_CHECK(ksize == 3 && !resid, "upsample op: 3x3 without residual only");
-      Split a = b.act_split(xt, nullptr, "", 0.f, false, XF_SAME);
-      PackedW& pw = W_up(&tm.m, "w");
+      Split a = b.act_split(xt, nullptr, "", 0.f, false, XF_SAME, nullptr, f8);
+      PackedW& pw = W_up(&tm.m, "w", f8);
       for (int par = 0; par < 4; ++par) {
-        Builder::ASrc src{a, Cin, W_, H, B, 3 + par};
+        Builder::ASrc src{a, Cin, W_, H, B, 3 + par, f8};
         Op& op = b.conv_gemm(src, pw, nullptr, nullptr, H, W_, Cout, par * 4 * pw.rows);
-        b.out_f32(op, out, Cout, bias, 0, nullptr, 0);
+        b.out_f32(op, out, Cout, bias, bias_ld, nullptr, 0);
         op.g.up_mode = 1;
         op.g.up_py = par >> 1;
         op.g.up_px = par & 1;
       }
     } else {
       const int layout = stride == 2 ? XF_S2D : XF_SAME;
-      Split a = b.act_split(xt, nullptr, "", 0.f, false, layout);
+      Split a = b.act_split(xt, nullptr, "", 0.f, false, layout, nullptr, f8);
       const int Ho = H / stride, Wo = W_ / stride;
-      Builder::ASrc src{a, Cin, Wo, Ho, stride == 2 ? 4 * B : B, ksize == 1 ? 0 : (stride == 2 ? 2 : 1)};
-      PackedW& pw = W(&tm.m, "w", {"w"});
+      Builder::ASrc src{a, Cin, Wo, Ho, stride == 2 ? 4 * B : B, ksize == 1 ? 0 : (stride == 2 ? 2 : 1), f8};
+      PackedW& pw = W(&tm.m, "w", {"w"}, 0, f8);
       Op& op = b.conv_gemm(src, pw, nullptr, nullptr, Ho, Wo, Cout);
       if (force_bn) {
         PF_CHECK(Cout % force_bn == 0, "force_bn does not divide Cout");
@@ -1929,7 +2014,7 @@ int pf_op_conv2d_nhwc(const float* x, int32_t B, int32_t H, int32_t W_, int32_t 
         op.g.seg[0].b_hi = mp.first;
         op.g.seg[0].b_lo = mp.second;
       }
-      b.out_f32(op, out, Cout, bias, 0, resid, Cout);
+      b.out_f32(op, out, Cout, bias, bias_ld, resid, Cout);
     }
     run_plan(&tm.m, plan, nullptr, nullptr, nullptr, nullptr, s);
     PF_CUDA(cudaStreamSynchronize(s));

@@ -4,8 +4,11 @@ Same constructor and attributes (ddpm/__init__.py:16-34: fp32 ``linspace(1e-4, 0
 a buffer; ``alpha`` / ``alpha_bar`` / ``sigma2`` as plain attributes).  ``p_sample`` evaluates
 ``eps_model(xt, t)`` (any CUDA ``nn.Module``) and applies the reverse step
 ``(xt - (1-alpha)/sqrt(1-alpha_bar) eps)/sqrt(alpha) + sqrt(beta) noise`` (:66-88, noise is added even
-at t = 0) in one ``pf_sample_step_ddpm_legacy`` kernel.  Unlike the reference, the tables follow the
-model to the GPU (the reference's plain attributes stay on the CPU).
+at t = 0) in one ``pf_sample_step_ddpm_legacy`` kernel.  ``beta`` is a registered buffer and follows
+``.to(device)``; ``alpha`` / ``alpha_bar`` / ``sigma2`` are plain attributes exactly as in the reference
+ -- the step kernels read host copies of the per-step scalars made once here.
+``loss`` (training, train/train_ddpm.py) is the reference's expression over the differentiable path of
+the eps-model (``ddpm.unet.UNet`` switches to its PyTorch graph when gradients are enabled).
 """
 from __future__ import annotations
 
@@ -37,8 +40,18 @@ class DenoiseDiffusion(nn.Module):
 
     @staticmethod
     def _uniform_t(t: torch.Tensor) -> Optional[int]:
+        """The common timestep of the batch, or None if the entries differ.  This reads ``t`` back to the
+        host (one device->host copy per call): the legacy API passes the step only as a tensor
+        (ddpm/__init__.py:66), and the per-step scalars of the fused kernel live on the host."""
         tl = t.tolist()
         return int(tl[0]) if all(v == tl[0] for v in tl) else None
+
+    def q_xt_x0(self, x0: torch.Tensor, t: torch.Tensor):
+        """Mean and variance of q(x_t | x_0) (ddpm/__init__.py:36-48)."""
+        from polyffusion_b200.ddpm.utils import gather
+
+        ab = gather(self.alpha_bar.to(t.device), t)
+        return ab**0.5 * x0, 1 - ab
 
     @torch.no_grad()
     def q_sample(self, x0: torch.Tensor, t: torch.Tensor, eps: Optional[torch.Tensor] = None):
@@ -71,5 +84,13 @@ class DenoiseDiffusion(nn.Module):
             outs.append(xp)
         return torch.cat(outs)
 
-    def loss(self, *args, **kwargs):
-        raise NotImplementedError("training loss is out of scope for polyffusion_b200 (sampling hot path only)")
+    def loss(self, x0: torch.Tensor, noise: Optional[torch.Tensor] = None):
+        """Simplified DDPM loss (ddpm/__init__.py:90-110): uniform t per sample, MSE(noise, eps_theta)."""
+        batch_size = x0.shape[0]
+        t = torch.randint(0, self.n_steps, (batch_size,), device=x0.device, dtype=torch.long)
+        if noise is None:
+            noise = torch.randn_like(x0)
+        mean, var = self.q_xt_x0(x0, t)
+        xt = mean + (var**0.5) * noise
+        eps_theta = self.eps_model(xt, t)
+        return torch.nn.functional.mse_loss(noise, eps_theta)

@@ -79,8 +79,26 @@ class LatentDiffusion(nn.Module):
             return out
         return ab**0.5 * x0 + ((1 - ab) ** 0.5) * eps
 
-    def loss(self, *args, **kwargs):
-        raise NotImplementedError(
-            "polyffusion_b200 covers the sampling hot path; the training loss "
-            "(latent_diffusion.py:203-240) is out of scope (SURVEY.md section 8f, rank 4)"
-        )
+    def q_xt_x0(self, x0: torch.Tensor, t: torch.Tensor):
+        """Mean and variance of q(x_t | x_0) (latent_diffusion.py:149-162)."""
+        ab = self.alpha_bar.gather(-1, t).reshape(-1, 1, 1, 1)
+        return ab**0.5 * x0, 1 - ab
+
+    def loss(self, x0: torch.Tensor, cond: torch.Tensor, noise: Optional[torch.Tensor] = None,
+             cond_concat: Optional[torch.Tensor] = None):
+        """Simplified DDPM loss, statement for statement latent_diffusion.py:203-240: one uniform
+        t per sample, x_t = q_sample(x0, t, noise), MSE between the noise and eps_theta(x_t, t, cond).
+        In training mode the eps-model runs its differentiable PyTorch graph (unet_torch.py); under
+        ``no_grad`` / ``eval`` (validation) it runs the CUDA plan."""
+        batch_size = x0.shape[0]
+        t = torch.randint(0, self.n_steps, (batch_size,), device=x0.device, dtype=torch.long)
+        if self.first_stage_model is not None:
+            x0 = self.autoencoder_encode(x0)
+        if noise is None:
+            noise = torch.randn_like(x0)
+        mean, var = self.q_xt_x0(x0, t)
+        xt = mean + (var**0.5) * noise
+        if cond_concat is not None:
+            xt = torch.concat([xt, cond_concat], dim=1)
+        eps_theta = self.eps_model(xt, t, cond)
+        return torch.nn.functional.mse_loss(noise, eps_theta)

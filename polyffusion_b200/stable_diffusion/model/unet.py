@@ -4,7 +4,9 @@ Same constructor signature (unet.py:35-47), same parameter names / shapes / cons
 reference checkpoints load with ``load_state_dict`` and a fixed seed gives the same random
 initialisation), same ``forward(x, time_steps, cond)`` contract (unet.py:171-196).  The arithmetic
 is not PyTorch: ``forward`` hands the three tensors to ``libpf_b200.so`` (``pf_unet_forward``), which
-replays a static plan of hand-written sm_100a kernels.  CUDA tensors only; no autograd.
+replays a static plan of hand-written sm_100a kernels (CUDA tensors only, no CPU fallback).  When
+gradients are required (training: ``LatentDiffusion.loss`` under the reference's ``learner.py``), the
+same parameters are evaluated by the differentiable PyTorch graph in ``unet_torch.py`` instead.
 """
 from __future__ import annotations
 
@@ -146,11 +148,35 @@ class UNetModel(nn.Module):
 
     def forward(self, x: torch.Tensor, time_steps: torch.Tensor, cond: torch.Tensor):
         """eps_theta(x_t, t, c): x [B,C,H,W], time_steps [B] (long), cond [B,n_cond,d_cond]."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and (
-            x.requires_grad or self.training
-        ):
-            raise NotImplementedError(
-                "polyffusion_b200.UNetModel implements the inference/sampling hot path only "
-                "(call under torch.no_grad() with model.eval()); training is out of scope"
-            )
+        if self._wants_autograd(x, cond):
+            from polyffusion_b200.stable_diffusion.model.unet_torch import unet_forward_torch
+
+            return unet_forward_torch(self, x, time_steps, cond)
         return self.engine.forward(x, time_steps, cond)
+
+    def _wants_autograd(self, x: torch.Tensor, cond: torch.Tensor) -> bool:
+        """True when the caller needs a differentiable result: grad mode is on and either the module is
+        in training mode with trainable parameters, or an input requires grad.  Sampling (the samplers
+        are ``@torch.no_grad()``, inference_sdf.py calls ``model.eval()``) never satisfies this."""
+        if not torch.is_grad_enabled():
+            return False
+        if x.requires_grad or (cond is not None and cond.requires_grad):
+            return True
+        return self.training and any(p.requires_grad for p in self.parameters())
+
+    # the engine holds a ctypes handle and device buffers: never copied / pickled with the module
+    # (copy.deepcopy for EMA, torch.save(model)); the copy builds its own engine lazily
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            object.__setattr__(new, k, None if k == "_engine" else copy.deepcopy(v, memo))
+        return new

@@ -70,7 +70,7 @@ def run(conv_scheme, lin_scheme, sd, cfg, x, t, c):
     finally:
         uo.F = RF
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     from polyffusion_b200.stable_diffusion.model.unet import UNetModel
     torch.manual_seed(0)
     kw = dict(in_channels=2, out_channels=2, channels=64, n_res_blocks=2, attention_levels=[2, 3],
@@ -90,3 +90,56 @@ if __name__ == "__main__":
         d = (y - ref).abs()
         ok = (d <= 1e-4 + 1e-3 * ref.abs()).double().mean()
         print(f"conv={cs:10s} lin={ls:8s} max {d.max():.3e} rms {d.pow(2).mean().sqrt():.3e} within-tol {100*ok:.3f}%  {STATS}")
+
+
+def sensitivity():
+    """which convolutions contribute most of the f16f8 error at the output?"""
+    from polyffusion_b200.stable_diffusion.model.unet import UNetModel
+    torch.manual_seed(0)
+    kw = dict(in_channels=2, out_channels=2, channels=64, n_res_blocks=2, attention_levels=[2, 3],
+              channel_multipliers=[1, 2, 4, 4], n_heads=4, tf_layers=1, d_cond=512)
+    sd = UNetModel(**kw).state_dict()
+    cfg = uo.UNetCfg(d_cond=512)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 2, 128, 128, generator=g)
+    c = torch.randn(2, 1, 512, generator=g)
+    t = torch.tensor([999, 3])
+    ref = run("fp32", "fp32", sd, cfg, x, t, c).double()
+
+    class Sel(FProxy):
+        def __init__(self, pred):
+            super().__init__("fp16_f8", "bf16x3")
+            self.alt = make("bf16x3")
+            self.pred = pred
+            self.n = 0
+        def conv2d(self, x, w, b=None, stride=1, padding=0):
+            if w.shape[1] < 16 or w.shape[0] < 16:
+                return RF.conv2d(x, w, b, stride=stride, padding=padding)
+            i = self.n
+            self.n += 1
+            p = self.cp if self.pred(i, x, w) else self.alt
+            y = p(lambda a, ww: RF.conv2d(a, ww, None, stride=stride, padding=padding), x, w)
+            return y if b is None else y + b[None, :, None, None]
+
+    def go(name, pred):
+        px = Sel(pred)
+        uo.F = px
+        try:
+            y = uo.unet_forward(sd, cfg, x, t, c).double()
+        finally:
+            uo.F = RF
+        d = (y - ref).abs()
+        print(f"{name:40s} convs={px.n} max {d.max():.3e} rms {d.pow(2).mean().sqrt():.3e}")
+        return px.n
+
+    n = go("all f8", lambda i, x, w: True)
+    go("none f8 (bf16x3)", lambda i, x, w: False)
+    for k in (2, 4, 8, 16):
+        go(f"f8 except last {k} convs", lambda i, x, w, k=k: i < n - k)
+    go("f8 only at 128x128", lambda i, x, w: x.shape[-1] == 128)
+    go("f8 except 128x128", lambda i, x, w: x.shape[-1] != 128)
+    go("f8 only 3x3", lambda i, x, w: w.shape[-1] == 3)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sens":
+    sensitivity()
