@@ -10,8 +10,10 @@ torch.randn draws the reference makes per step.  Every step costs the same irres
 
     samples/sec = N_gpus * 64 / (1000 * seconds_per_step + seconds_for_the_final_all_gather)
 
-`value` is timed with inputs resident in HBM; `e2e` goes through the public Python API with HOST
-(pinned) buffers: H2D of x_t/cond, SDFSampler.p_sample-equivalent step, D2H of x_{t-1}, every step.
+`value` is timed with inputs resident in HBM; `e2e` runs the SAME step function with HOST (pinned)
+buffers: H2D of x_t/cond, the step, D2H of x_{t-1}, every step.  `sustained` repeats the step back to
+back for >= 3 s.  --config 2/3/4 time BASELINE.json configs[2..4] (DDIM-50, CFG scale 5, one window-step
+of the song-batched autoregressive driver) on the same contract.
 Inputs (8.4 MB x_t + 8.4 MB noise x2 + ~2.5 GB of activations) exceed nothing cache-wise: the
 activation working set of one step is ~40x the 126 MB L2, so L2 is effectively flushed between
 steps ("l2": "inputs larger than L2").
@@ -61,12 +63,13 @@ def load_gemm_traffic():
     """DRAM bytes moved by the tcgen05 GEMM launches of ONE step, from the newest committed ncu launch
     list (profiles/*_gemm_traffic.json, written by tools/ncu_launches_step.py); None if absent."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")), key=os.path.getmtime)
     if not files:
-        return None, None
+        return None, None, None
     with open(files[-1]) as f:
         d = json.load(f)
-    return d["gemm_dram_bytes_read"] + d["gemm_dram_bytes_write"], os.path.relpath(files[-1], ROOT)
+    return (d["gemm_dram_bytes_read"] + d["gemm_dram_bytes_write"], os.path.relpath(files[-1], ROOT),
+            d.get("kernel_source_hash"))
 
 
 class ClockSampler:
@@ -172,6 +175,35 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+# --config N selects BASELINE.json configs[N]; configs[1] is the one the metric is quoted on (default).
+CONFIGS = {
+    1: dict(workload=WORKLOAD, metric=METRIC, unit=UNIT, d_cond=D_COND, kind="ddpm", scale=1.0, units_per_gpu=B_PER_GPU,
+            steps_per_unit=DDPM_STEPS, evals_per_step=1),
+    2: dict(workload="configs[2]: sdf_txt conditional, batch=64 per GPU, DDIM 50 steps eta=0.0 (DDIMSampler.sample path)",
+            metric="8bar_pianoroll_samples_per_sec_ddim50", unit=UNIT, d_cond=1024, kind="ddim", scale=1.0,
+            units_per_gpu=B_PER_GPU, steps_per_unit=50, evals_per_step=1),
+    3: dict(workload="configs[3]: sdf_chd8bar uncond_scale=5 classifier-free guidance (2 UNet evals per step), "
+                     "batch=64 per GPU (512 over 8 GPUs; UNet batch 128), 1000-step DDPM",
+            metric="8bar_pianoroll_samples_per_sec_ddpm1000_cfg5", unit=UNIT, d_cond=D_COND, kind="ddpm", scale=5.0,
+            units_per_gpu=B_PER_GPU, steps_per_unit=DDPM_STEPS, evals_per_step=2),
+    4: dict(workload="configs[4]: autoregressive inpaint (inpaint_type=below), 10 segments per song = 19 windows, "
+                     "32 songs per GPU (256 over 8 GPUs), 1000-step DDPM per window; one step = one (window, step) "
+                     "over the 32 songs",
+            metric="songs_per_sec_autoreg10_ddpm1000", unit="songs/s", d_cond=D_COND, kind="autoreg", scale=1.0,
+            units_per_gpu=32, steps_per_unit=19 * DDPM_STEPS, evals_per_step=1),
+}
+
+
+def kernel_source_hash():
+    """sha1 over the CUDA sources: the committed ncu traffic file records the hash it was measured at."""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(glob.glob(os.path.join(ROOT, "polyffusion_b200", "csrc", "*.cu*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -179,6 +211,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: polyffusion_b200 has no CPU fallback "
                            "(use --impl reference for the CPU baseline)")
+    cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -193,35 +226,59 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    from polyffusion_b200.sampler_ddim import DDIMSampler
     from polyffusion_b200.sampler_sdf import SDFSampler
     from polyffusion_b200.stable_diffusion.latent_diffusion import LatentDiffusion
     from polyffusion_b200.stable_diffusion.model.unet import UNetModel
 
     torch.manual_seed(0)  # identical weights on every rank
-    unet = UNetModel(**sdf_kwargs()).eval()
+    kw = sdf_kwargs()
+    kw["d_cond"] = cfg["d_cond"]
+    unet = UNetModel(**kw).eval()
     ldm = LatentDiffusion(unet, None, 0.18215, DDPM_STEPS, 0.00085, 0.012).to(dev)
-    sampler = SDFSampler(ldm)
-    B = B_PER_GPU
+    B = cfg["units_per_gpu"]  # chains advanced by one step (samples; songs for configs[4])
     torch.manual_seed(1000 + rank)  # per-rank noise stream
-    cond = torch.randn(B, 1, D_COND, device=dev)
+    cond = torch.randn(B, 1, cfg["d_cond"], device=dev)
+    uncond = -torch.ones(B, 1, cfg["d_cond"], device=dev) if cfg["scale"] != 1.0 else None
     orig = torch.zeros(B, 2, 128, 128, device=dev)
     mask = torch.zeros_like(orig)
-    x = sampler.q_sample(orig, DDPM_STEPS - 1, torch.randn(B, 2, 128, 128, device=dev))
+    if cfg["kind"] == "autoreg":
+        # one window of the song-batched autoregressive driver (autoreg.py): the first half of every
+        # window is the known region generated by the previous window, "below" mask on the rest
+        mask[:, :, :64, :] = 1.0
+        mask[:, :, 64:, :60] = 1.0
+        orig[:, 0, ::4, 72] = 1.0
+    if cfg["kind"] == "ddim":
+        sampler = DDIMSampler(ldm, 50, "uniform", 0.0)
+        x0 = torch.randn(B, 2, 128, 128, device=dev)
+        n_idx = len(sampler.time_steps)
 
-    def one_step(xx, step):
-        ts = xx.new_full((B,), step, dtype=torch.long)
-        noise_kn = torch.randn_like(orig) if step > 0 else None
-        xx, _, _ = sampler._step(xx, cond, ts, step, orig=orig, mask=mask, noise_kn=noise_kn, want_aux=False)
-        return xx
+        def step_fn(xx, i):  # i counts down; DDIM index wraps inside the 50-step schedule
+            index = i % n_idx
+            ts = xx.new_full((B,), int(sampler.time_steps[index]), dtype=torch.long)
+            return sampler._step(xx, cond, ts, index, want_aux=False)[0]
+    else:
+        sampler = SDFSampler(ldm)
+        x0 = sampler.q_sample(orig, DDPM_STEPS - 1, torch.randn(B, 2, 128, 128, device=dev))
+
+        def step_fn(xx, i):
+            # exactly the body of SDFSampler.paint's loop (sampler_sdf.py:313-336): known-region noise,
+            # UNet evaluation(s), fused CFG / x0 / mean / noise / RePaint-blend epilogue
+            step = max(i % DDPM_STEPS, 1)
+            ts = xx.new_full((B,), step, dtype=torch.long)
+            noise_kn = torch.randn_like(orig)
+            return sampler._step(xx, cond, ts, step, uncond_scale=cfg["scale"], uncond_cond=uncond, orig=orig,
+                                 mask=mask, noise_kn=noise_kn, want_aux=False)[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    x = x0
     step_id = DDPM_STEPS - 1
     for _ in range(max(args.warmup, 3)):
-        x = one_step(x, step_id)
+        x = step_fn(x, step_id)
         step_id -= 1
     launches_per_eval = unet.engine.launch_count()
 
@@ -233,12 +290,31 @@ def run_gpu_arm(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        x = one_step(x, max(step_id, 1))
+        x = step_fn(x, step_id)
         step_id -= 1
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     clock_info = clocks.stop() if rank == 0 else None
+
+    # ---- sustained: the same step back to back for >= 3 s (what a 1000-step run actually sees once the
+    # board has reached its power limit), with its own clock record
+    sus_steps, sus_ms, sus_clock = 0, 0.0, None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms_total / args.steps, 1e-3)) + 1)
+        sclk = ClockSampler(local_rank)
+        if rank == 0:
+            sclk.start()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_sus):
+            x = step_fn(x, step_id)
+            step_id -= 1
+        s1.record()
+        barrier()
+        sus_steps, sus_ms = n_sus, s0.elapsed_time(s1)
+        sus_clock = sclk.stop() if rank == 0 else None
 
     # ---- final all-gather of the finished samples (the path's only collective)
     gather_ms = 0.0
@@ -253,37 +329,42 @@ def run_gpu_arm(args):
         barrier()
         gather_ms = g0.elapsed_time(g1)
 
-    # ---- e2e: host buffers, H2D + step + D2H every step, through the public sampler API
+    # ---- e2e: the SAME step through the public sampler API with HOST (pinned) buffers: x_t and cond go
+    # host -> device and x_{t-1} comes back device -> host every step, inside the timed region
     x_host = x.detach().cpu().pin_memory()
     cond_host = cond.detach().cpu().pin_memory()
     out_host = torch.empty_like(x_host).pin_memory()
+    cond_dev = cond
 
-    def e2e_step(step):
+    def e2e_step(i):
+        nonlocal cond
         xd = x_host.to(dev, non_blocking=True)
-        cd = cond_host.to(dev, non_blocking=True)
-        ts = xd.new_full((B,), step, dtype=torch.long)
-        xp, _, _ = sampler.p_sample(xd, cd, ts, step)
-        out_host.copy_(xp, non_blocking=True)
+        cond = cond_host.to(dev, non_blocking=True)
+        out_host.copy_(step_fn(xd, i), non_blocking=True)
 
-    for _ in range(3):
-        e2e_step(500)
+    for i in range(3):
+        e2e_step(500 - i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     n_e2e = max(3, min(args.steps, 10))
     for i in range(n_e2e):
-        e2e_step(500 - i)
+        e2e_step(490 - i)
     e1.record()
     barrier()
+    cond = cond_dev
     e2e_ms = e0.elapsed_time(e1) / n_e2e
 
-    # ---- per-kernel breakdown of one step (CUDA events around every launch of the plan)
+    # ---- per-kernel breakdown of one UNet evaluation (CUDA events around every launch of the plan)
     prof = {}
-    ts = x.new_full((B,), 500, dtype=torch.long)
+    Bp = B * cfg["evals_per_step"]
+    xp = torch.randn(Bp, 2, 128, 128, device=dev)
+    cp = torch.randn(Bp, 1, cfg["d_cond"], device=dev)
+    ts = xp.new_full((Bp,), 500, dtype=torch.long)
     gemm_ms, gemm_flops, other_ms, gemm_launches, attn_ms, attn_flops = 0.0, 0.0, 0.0, 0, 0.0, 0.0
     n_prof = 3
     for _ in range(n_prof):
-        unet.engine.forward(x, ts, cond, profile=prof)
+        unet.engine.forward(xp, ts, cp, profile=prof)
         for ms, fl, kd in zip(prof["ms"], prof["flops"], prof["kind"]):
             if kd == 0:  # gemm_tc_kernel
                 gemm_ms += ms
@@ -302,55 +383,71 @@ def run_gpu_arm(args):
     gemm_launches //= n_prof
 
     # ---- reduce over ranks (max time)
-    vals = torch.tensor([ms_total, gather_ms, e2e_ms], device=dev, dtype=torch.float64)
+    vals = torch.tensor([ms_total, gather_ms, e2e_ms, sus_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    ms_total, gather_ms, e2e_ms = (float(v) for v in vals.tolist())
+    ms_total, gather_ms, e2e_ms, sus_ms = (float(v) for v in vals.tolist())
     ms_per_step = ms_total / args.steps
-    value = world * B / (DDPM_STEPS * ms_per_step / 1e3 + gather_ms / 1e3)
-    e2e_value = world * B / (DDPM_STEPS * e2e_ms / 1e3 + gather_ms / 1e3)
+    spu = cfg["steps_per_unit"]
+    rate = lambda ms: world * B / (spu * ms / 1e3 + gather_ms / 1e3)
+    value, e2e_value = rate(ms_per_step), rate(e2e_ms)
 
     if rank == 0:
         peaks = load_peaks()
-        traffic, traffic_src = load_gemm_traffic()
+        traffic, traffic_src, traffic_hash = load_gemm_traffic()
+        traffic_note = None
+        if traffic is not None and traffic_hash != kernel_source_hash():
+            traffic_note = (f"{traffic_src} was captured at kernel sources {traffic_hash}, current {kernel_source_hash()}: "
+                            "stale, not reported (re-run tools/gpu_final.sh)")
+            traffic = None
+        elif traffic is not None:
+            traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM launches of one step "
+                            f"({traffic_src}, same kernel sources)")
         achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        cpu_value, cpu_sec, cores = cpu_port_samples_per_sec(4, 3, 1) if world == 1 and not args.no_cpu else (None, None, None)
+        step_tflop = GFLOP_PER_SAMPLE_EVAL * Bp / 1e3
+        cpu_value, cpu_sec, cores = (cpu_port_samples_per_sec(4, 3, 1)
+                                     if world == 1 and not args.no_cpu and args.config == 1 else (None, None, None))
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16+f8 convolutions (fp16 product + e4m3 cross terms), bf16x3 linears/attention; fp32 accumulate",
             "data": "synthetic",
             "config": {
-                "workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B,
+                "workload": cfg["workload"], "batch_per_gpu": B, "global_batch": world * B,
                 "parallelism": f"dp{world} (independent chains, one all-gather at the end)",
                 "l2": "inputs larger than L2 (per-step activation working set >> 126 MB)",
                 "allgather_ms": gather_ms,
-                "unet_eval_algorithmic_tflop": GFLOP_PER_SAMPLE_EVAL * B / 1e3,
-                "unet_algorithmic_tflops": GFLOP_PER_SAMPLE_EVAL * B / 1e3 / (ms_per_step / 1e3),
-                "precision_note": "3 tcgen05 MMAs per algorithmic product (hi*hi + lo*hi + hi*lo): "
-                                  "algorithmic FLOP/s is capped at 1/3 of issued tensor FLOP/s",
+                "unet_eval_algorithmic_tflop": step_tflop,
+                "unet_algorithmic_tflops": step_tflop / (ms_per_step / 1e3),
+                "precision_note": "convolutions: 1 fp16 MMA + 1 fp8 MMA at twice the rate per product (2 tensor-time "
+                                  "units); linears / attention: 3 bf16 MMAs per product (hi*hi + lo*hi + hi*lo)",
+                "conv_operands": os.environ.get("PF_CONV_F8_MAX_HW", "f16f8 everywhere (default)"),
                 "step_breakdown_ms": {"tcgen05_gemm": gemm_ms, "tcgen05_attention": attn_ms,
                                       "other_kernels": other_ms},
                 "attention_algorithmic_tflops": (attn_flops / (attn_ms * 1e-3) / 1e12) if attn_ms > 0 else None,
             },
             "clocks": clock_info,
-            "e2e": {"value": e2e_value, "unit": UNIT,
+            "sustained": None if sus_steps == 0 else {
+                "value": rate(sus_ms / sus_steps), "unit": cfg["unit"], "ms_per_step": sus_ms / sus_steps,
+                "steps": sus_steps, "seconds": sus_ms / 1e3, "clocks": sus_clock,
+                "note": "same step, back to back; the number a 1000-step run sees at the board power limit"},
+            "e2e": {"value": e2e_value, "unit": cfg["unit"],
                     "h2d_bytes_per_step": x_host.numel() * 4 + cond_host.numel() * 4,
-                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms},
-            "gpu_launches": args.steps * (launches_per_eval + 1),
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms,
+                    "note": "same step function as `value`, x_t / cond from pinned host memory, x_{t-1} back to the host"},
+            "gpu_launches": args.steps * (cfg["evals_per_step"] * 0 + launches_per_eval + 1),
             "roofline": {
-                "bound": "tensor", "kernel": "gemm_tc_kernel<BN> (all tcgen05 GEMM launches of one step)",
+                "bound": "tensor", "kernel": "gemm_tc*_kernel (all tcgen05 GEMM launches of one step)",
                 "achieved": achieved_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tf_sust"], "traffic": traffic,
-                "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM launches of one "
-                                 f"step ({traffic_src})") if traffic else None,
+                "frac": achieved_tf / peaks["tf_sust"], "traffic": traffic, "traffic_note": traffic_note,
                 "launches_per_step": gemm_launches,
                 "algorithmic_flops_per_step": gemm_flops, "kernel_ms_per_step": gemm_ms,
                 "peak_source": "bf16 dense sustained, " + peaks["source"],
-                "issued_frac": 3 * achieved_tf / peaks["tf_sust"],
+                "note": "achieved = algorithmic FLOP (2*M*N*K per product) / measured GEMM time; the split-precision "
+                        "schemes issue 2 (f16f8) or 3 (bf16x3) tensor-time units per algorithmic product",
                 # the whole step (GEMMs + attention + HBM-bound transforms + step epilogue) on the same scale
-                "whole_step_frac": GFLOP_PER_SAMPLE_EVAL * B / 1e3 / (ms_per_step / 1e3) / peaks["tf_sust"],
-                "whole_step_issued_frac": 3 * GFLOP_PER_SAMPLE_EVAL * B / 1e3 / (ms_per_step / 1e3) / peaks["tf_sust"],
+                "whole_step_frac": step_tflop / (ms_per_step / 1e3) / peaks["tf_sust"],
             },
         }
         if cpu_value is not None:
@@ -371,6 +468,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS),
+                    help="BASELINE.json configs[N]; 1 (default) is the configuration the metric is quoted on")
+    ap.add_argument("--sustain-seconds", type=float, default=3.0,
+                    help="length of the extra back-to-back run reported under `sustained` (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

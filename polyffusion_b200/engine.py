@@ -3,14 +3,17 @@
 Lifetime: created lazily on the first CUDA forward; weights are pushed through
 ``pf_unet_set_weight`` / ``pf_unet_finalize`` (the library keeps its own packed split-bf16 copy) and
 re-pushed whenever a parameter's storage or version counter changes (``load_state_dict``, ``.to()``,
-optimizer steps).  Workspaces are cached per (batch, n_cond, H, W).
+optimizer steps).  Workspaces / CUDA graphs are cached per (batch, n_cond, H, W) in a small LRU
+(PF_ENGINE_CACHE entries, default 4: a ragged last batch, the CFG 2B evaluation, the autoregressive
+song batch), so a workload with many batch sizes cannot pile up activation workspaces.
 """
 from __future__ import annotations
 
 import ctypes
 import math
 import os
-from typing import Dict, Tuple
+from collections import OrderedDict
+from typing import Tuple
 
 import torch
 
@@ -24,9 +27,9 @@ class UNetEngine:
         self.handle = ctypes.c_void_p()
         self.device = None
         self._stamp = None
-        self._workspaces: Dict[Tuple[int, int, int, int], torch.Tensor] = {}
-        self._graphs: Dict[Tuple[int, int, int, int], tuple] = {}
-        self._keep = []
+        self._workspaces: "OrderedDict[Tuple[int, int, int, int], torch.Tensor]" = OrderedDict()
+        self._graphs: "OrderedDict[Tuple[int, int, int, int], tuple]" = OrderedDict()
+        self._cache_entries = max(1, int(os.environ.get("PF_ENGINE_CACHE", "4")))
         # replay each (batch, n_cond, H, W) evaluation as a CUDA graph (measured ~3 % faster than the
         # 261 individual launches); PF_CUDA_GRAPH=0 disables it
         self.use_graph = os.environ.get("PF_CUDA_GRAPH", "1") != "0"
@@ -54,6 +57,16 @@ class UNetEngine:
 
     def _params_stamp(self):
         return tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+
+    def _touch(self, key) -> None:
+        """Mark `key` most recently used and evict the oldest (batch, n_cond, H, W) entries: graph first
+        (it replays launches that point into the workspace), then the workspace."""
+        for cache in (self._graphs, self._workspaces):
+            if key in cache:
+                cache.move_to_end(key)
+        while len(self._workspaces) > self._cache_entries:
+            old, _ = self._workspaces.popitem(last=False)
+            self._graphs.pop(old, None)
 
     def sync_weights(self, device: torch.device, force: bool = False) -> None:
         """(Re)pack the module's current parameters into the library."""
@@ -125,6 +138,7 @@ class UNetEngine:
         return self._forward_eager(key, x, t, cond, out, profile)
 
     def _forward_graph(self, key, x, t, cond, out):
+        self._touch(key)
         entry = self._graphs.get(key)
         if entry is None:
             # static buffers + one eager call (builds the plan) + capture
@@ -153,12 +167,15 @@ class UNetEngine:
         dev = x.device
         with torch.cuda.device(dev):
             ws = self._workspaces.get(key)
+            if ws is not None:
+                self._workspaces.move_to_end(key)
             if ws is None:
                 nbytes = lib().pf_unet_workspace_bytes(self.handle, B, n_cond, H, W)
                 if nbytes == 0:
                     raise PfError(lib().pf_last_error().decode("utf-8", "replace"))
                 ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
                 self._workspaces[key] = ws
+                self._touch(key)
             base = (ws.data_ptr() + 1023) // 1024 * 1024
             if out is None:
                 out = torch.empty((B, self.cfg["out_channels"], H, W), dtype=torch.float32, device=dev)

@@ -90,11 +90,19 @@ def test_cpu_tensors_fail_loudly():
         s.q_sample(torch.zeros(1, 2, 8, 8), 3, torch.zeros(1, 2, 8, 8))
 
 
-def test_training_is_rejected():
-    m = build_unet(512).train()
-    x = torch.zeros(1, 2, 128, 128, requires_grad=True)
-    with pytest.raises(NotImplementedError):
-        m(x, torch.zeros(1, dtype=torch.long), torch.zeros(1, 1, 512))
+def test_forward_dispatch_between_autograd_graph_and_cuda_plan():
+    """Gradients required -> differentiable PyTorch graph (tests/test_training_path.py checks its values);
+    no_grad / eval on CPU tensors -> the CUDA plan, which refuses CPU tensors (no CPU fallback)."""
+    from polyffusion_b200._lib import PfError
+
+    m = build_unet(512)
+    x, t, c = torch.zeros(1, 2, 128, 128), torch.zeros(1, dtype=torch.long), torch.zeros(1, 1, 512)
+    assert m.train()._wants_autograd(x, c) and not m.eval()._wants_autograd(x, c)
+    assert m._wants_autograd(x.clone().requires_grad_(True), c)
+    with torch.no_grad():
+        assert not m.train()._wants_autograd(x, c)
+        with pytest.raises(PfError):
+            m.eval()(x, t, c)
 
 
 def test_install_dropin_aliases_reference_import_paths():

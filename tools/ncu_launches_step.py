@@ -38,8 +38,12 @@ def main(path, out_txt, out_json, cmd):
         e[3] += d.get("dram__bytes_write.sum", 0.0)
     tot = sum(e[0] for e in agg.values())
     gemm = [e for k, e in agg.items() if k.startswith("gemm_tc")]
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import kernel_source_hash
     summary = {
         "command": cmd,
+        "kernel_source_hash": kernel_source_hash(),  # bench.py drops the traffic figure when the sources changed
         "launches_per_step": len(step),
         "step_us_sum_of_kernels_under_ncu": tot,
         "gemm_launches": sum(e[1] for e in gemm),
