@@ -248,27 +248,36 @@ def run_gpu_arm(args):
         mask[:, :, :64, :] = 1.0
         mask[:, :, 64:, :60] = 1.0
         orig[:, 0, ::4, 72] = 1.0
+    noise_mode = os.environ.get("PF_NOISE", "philox")
     if cfg["kind"] == "ddim":
         sampler = DDIMSampler(ldm, 50, "uniform", 0.0)
         x0 = torch.randn(B, 2, 128, 128, device=dev)
         n_idx = len(sampler.time_steps)
 
-        def step_fn(xx, i):  # i counts down; DDIM index wraps inside the 50-step schedule
-            index = i % n_idx
-            ts = xx.new_full((B,), int(sampler.time_steps[index]), dtype=torch.long)
-            return sampler._step(xx, cond, ts, index, want_aux=False)[0]
+        def run_steps(xx, start, n):  # n DDIM steps (sampler_ddim.py:145-163) from schedule index `start`
+            while n > 0:
+                k = min(n, start % n_idx + 1)
+                xx = sampler.advance(xx, cond, start % n_idx, k)
+                start, n = start - k, n - k
+            return xx
     else:
         sampler = SDFSampler(ldm)
         x0 = sampler.q_sample(orig, DDPM_STEPS - 1, torch.randn(B, 2, 128, 128, device=dev))
 
-        def step_fn(xx, i):
-            # exactly the body of SDFSampler.paint's loop (sampler_sdf.py:313-336): known-region noise,
-            # UNet evaluation(s), fused CFG / x0 / mean / noise / RePaint-blend epilogue
-            step = max(i % DDPM_STEPS, 1)
-            ts = xx.new_full((B,), step, dtype=torch.long)
-            noise_kn = torch.randn_like(orig)
-            return sampler._step(xx, cond, ts, step, uncond_scale=cfg["scale"], uncond_cond=uncond, orig=orig,
-                                 mask=mask, noise_kn=noise_kn, want_aux=False)[0]
+        def run_steps(xx, start, n):
+            # n iterations of SDFSampler.paint's loop body (sampler_sdf.py:313-336): known-region noise, UNet
+            # evaluation(s), CFG / x0 / mean / noise / RePaint-blend epilogue.  start stays >= n so that no
+            # slice reaches step 0 (which draws no noise)
+            start = n + start % (DDPM_STEPS - n)
+            return sampler.advance(xx, cond, start, n, orig=orig, mask=mask, uncond_scale=cfg["scale"],
+                                   uncond_cond=uncond)
+    # in-kernel Philox noise keyed by the GLOBAL sample index: the sharded run reproduces the 1-GPU samples
+    sampler.noise = noise_mode
+    sampler.seed = 20261017
+    sampler.sample0 = rank * B
+
+    def step_fn(xx, i):
+        return run_steps(xx, i, 1)
 
     def barrier():
         if world > 1:
@@ -277,9 +286,8 @@ def run_gpu_arm(args):
 
     x = x0
     step_id = DDPM_STEPS - 1
-    for _ in range(max(args.warmup, 3)):
-        x = step_fn(x, step_id)
-        step_id -= 1
+    x = run_steps(x, step_id, max(args.warmup, 3))
+    step_id -= max(args.warmup, 3)
     launches_per_eval = unet.engine.launch_count()
 
     # ---- timed region: device-resident inputs
@@ -289,9 +297,8 @@ def run_gpu_arm(args):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        x = step_fn(x, step_id)
-        step_id -= 1
+    x = run_steps(x, step_id, args.steps)  # ONE call of the public sampler API: K graph replays, no host work
+    step_id -= args.steps
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -308,9 +315,8 @@ def run_gpu_arm(args):
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for _ in range(n_sus):
-            x = step_fn(x, step_id)
-            step_id -= 1
+        x = run_steps(x, step_id, n_sus)
+        step_id -= n_sus
         s1.record()
         barrier()
         sus_steps, sus_ms = n_sus, s0.elapsed_time(s1)
@@ -423,6 +429,10 @@ def run_gpu_arm(args):
                 "precision_note": "convolutions: 1 fp16 MMA + 1 fp8 MMA at twice the rate per product (2 tensor-time "
                                   "units); linears / attention: 3 bf16 MMAs per product (hi*hi + lo*hi + hi*lo)",
                 "conv_operands": os.environ.get("PF_CONV_F8_MAX_HW", "f16f8 everywhere (default)"),
+                "noise": ("in-kernel Philox4x32-10 keyed by (seed, global sample index, element, step)"
+                          if noise_mode == "philox" else "torch.randn per step in the reference's order"),
+                "loop": "whole-step CUDA graph (UNet + fused step epilogue + device-side step counter)"
+                        if getattr(sampler, "fused_loop", False) and cfg["scale"] == 1.0 else "per-step launches",
                 "step_breakdown_ms": {"tcgen05_gemm": gemm_ms, "tcgen05_attention": attn_ms,
                                       "other_kernels": other_ms},
                 "attention_algorithmic_tflops": (attn_flops / (attn_ms * 1e-3) / 1e12) if attn_ms > 0 else None,
@@ -436,7 +446,9 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": x_host.numel() * 4 + cond_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms,
                     "note": "same step function as `value`, x_t / cond from pinned host memory, x_{t-1} back to the host"},
-            "gpu_launches": args.steps * (cfg["evals_per_step"] * 0 + launches_per_eval + 1),
+            # kernels of one step: the plan's launches (the step arithmetic lives in its last kernel) + the
+            # device-side counter advance; guided (CFG) steps launch the separate step kernel instead
+            "gpu_launches": args.steps * (launches_per_eval + 1),
             "roofline": {
                 "bound": "tensor", "kernel": "gemm_tc*_kernel (all tcgen05 GEMM launches of one step)",
                 "achieved": achieved_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",

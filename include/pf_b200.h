@@ -68,6 +68,54 @@ size_t pf_unet_workspace_bytes(pf_unet* h, int32_t batch, int32_t n_cond, int32_
 int pf_unet_forward(pf_unet* h, const float* x, const int64_t* time_steps, const float* cond,
                     int32_t batch, int32_t n_cond, int32_t height, int32_t width, float* out,
                     void* workspace, size_t workspace_bytes, pf_stream stream);
+/* One WHOLE reverse-diffusion step without host involvement (sampler_sdf.py:292-341, sampler_ddim.py:
+ * 104-166 / 301-362 loop bodies): the UNet evaluation with the step arithmetic applied to eps inside its
+ * last kernel (x0, posterior mean / DDIM direction, noise, RePaint blend with the re-noised known region),
+ * then index -= 1 and time_steps[b] = t_table[index] on the device.  Everything that changes from step to
+ * step lives in device memory, so a sampling loop is the replay of ONE captured CUDA graph:
+ *   index    device int32[2]: [0] row of `coef` / `t_table` of this step (DDPM: the step; DDIM: schedule
+ *            index), decremented by the call; [1] run nonce: the Philox key is seed + nonce * 0x9E3779B97F4A7C15
+ *   coef     device [n_index][8] fp32: c0..c4 of pf_step_args for every index, then kn_a, kn_b, 0
+ *   t_table  device [n_index] int64: timestep fed to the UNet at every index
+ *   x        x_t in, x_{t-1} out, NCHW [B, out_channels, H, W] (x_in is the UNet input: x itself, or x
+ *            concatenated with extra channels in a separate buffer)
+ *   noise / noise_kn  injected N(0,1) tensors (the reference's torch.randn order), or NULL: Philox4x32-10
+ *            normals keyed by (seed, sample0 + b, element, index) -- identical for any sharding of the batch
+ *            over ranks; orig / mask: RePaint known region or NULL.
+ * flags bit 0: skip the cond-only prologue (cross-attention vectors) -- pf_unet_prepare_cond was run for this
+ * cond tensor.  DDPM draws no noise at index 0 (sampler_sdf.py:152-153, 322-324). */
+typedef struct pf_fused_step {
+  int32_t kind;  /* 1 = DDPM (pf_sample_step_ddpm arithmetic), 2 = DDIM (pf_sample_step_ddim) */
+  int32_t flags;
+  int32_t* index;
+  const float* coef;
+  const int64_t* t_table;
+  float* x;
+  float* eps_out; /* optional */
+  const float* noise;
+  const float* noise_kn;
+  const float* orig;
+  const float* mask;
+  float temperature;
+  uint64_t seed;
+  int64_t sample0;
+} pf_fused_step;
+int pf_unet_forward_step(pf_unet* h, const float* x_in, int64_t* time_steps, const float* cond, int32_t batch,
+                         int32_t n_cond, int32_t height, int32_t width, const pf_fused_step* step,
+                         void* workspace, size_t workspace_bytes, pf_stream stream);
+/* Runs only the part of the plan that depends on `cond` alone (the n_cond == 1 cross-attention vectors
+ * to_out(to_v(cond)), unet_attention.py:186-212): once per sampling loop instead of once per step. */
+int pf_unet_prepare_cond(pf_unet* h, const float* cond, int32_t batch, int32_t n_cond, int32_t height,
+                         int32_t width, void* workspace, size_t workspace_bytes, pf_stream stream);
+/* Tabulates time_embed + every ResBlock emb_layers projection (unet.py:64-68, 151-169, 286-289) for the
+ * integer timesteps 0 .. n_steps-1 with the plan's own kernels (rows bit-identical to a forward at that t);
+ * later forwards gather one row per sample (timesteps are clamped to the table).  Reset by pf_unet_finalize. */
+int pf_unet_enable_time_lut(pf_unet* h, int32_t n_steps, pf_stream stream);
+/* out[b, i] = the Philox normal pf_unet_forward_step would draw for (seed, sample0 + b, element i, index,
+ * which: 0 = step noise, 1 = known-region noise); out [n_samples, per_sample] fp32. */
+int pf_fill_normal(float* out, int64_t n_samples, int64_t per_sample, uint64_t seed, int64_t sample0,
+                   int32_t index, int32_t which, pf_stream stream);
+
 /* Same as pf_unet_forward but brackets every kernel of the plan with CUDA events on `stream`,
  * synchronises, and reports per-launch milliseconds, algorithmic FLOPs (2*M*N*K for the tcgen05
  * GEMM launches, 0 otherwise) and the op kind (0 = tcgen05 GEMM, 1 = first conv, 2/3 = GroupNorm

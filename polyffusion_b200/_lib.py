@@ -34,6 +34,26 @@ class UNetCfg(Structure):
     ]
 
 
+class FusedStepArgs(Structure):
+    """pf_fused_step (include/pf_b200.h)."""
+    _fields_ = [
+        ("kind", c_int32),
+        ("flags", c_int32),
+        ("index", c_void_p),
+        ("coef", c_void_p),
+        ("t_table", c_void_p),
+        ("x", c_void_p),
+        ("eps_out", c_void_p),
+        ("noise", c_void_p),
+        ("noise_kn", c_void_p),
+        ("orig", c_void_p),
+        ("mask", c_void_p),
+        ("temperature", c_float),
+        ("seed", ctypes.c_uint64),
+        ("sample0", c_int64),
+    ]
+
+
 class StepArgs(Structure):
     _fields_ = [
         ("x", c_void_p),
@@ -74,6 +94,15 @@ SYMBOLS = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
          c_void_p, c_size_t, c_void_p],
     ),
+    "pf_unet_forward_step": (
+        c_int32,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(FusedStepArgs),
+         c_void_p, c_size_t, c_void_p],
+    ),
+    "pf_unet_prepare_cond": (
+        c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
+    "pf_unet_enable_time_lut": (c_int32, [c_void_p, c_int32, c_void_p]),
+    "pf_fill_normal": (c_int32, [c_void_p, c_int64, c_int64, ctypes.c_uint64, c_int64, c_int32, c_int32, c_void_p]),
     "pf_unet_forward_profiled": (
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,

@@ -749,6 +749,118 @@ void launch_small_linear(const float* in, long long ld_in, const float* W, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) + Box-Muller: counter = (element, global sample, index, stream),
+// key = seed.  One normal per call; the integer path is bit-exact against oracle/philox_oracle.py.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float philox_normal(unsigned long long seed, long long sample, uint32_t elem, int index,
+                                               int which) {
+  uint32_t r[4];
+  philox4x32_10(elem, static_cast<uint32_t>(sample), static_cast<uint32_t>(index), static_cast<uint32_t>(which),
+                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+  const float u1 = (static_cast<float>(r[0] >> 8) + 0.5f) * 5.9604644775390625e-08f;  // (0, 1), 2^-24 steps
+  const float u2 = (static_cast<float>(r[1] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+}
+
+// one element of the fused reverse step: e = eps at flat NCHW position i of sample b (i inside the sample)
+__device__ __forceinline__ void fused_step_apply(const FusedStep& fs, int b, long long per_sample, long long i,
+                                                 float e) {
+  const int idx = fs.index[0];
+  // Philox key of this run: seed + nonce * 2^64/phi; the nonce sits next to the index in device memory so
+  // that a captured graph draws fresh noise for every sampling run (polyffusion_b200/_loop.py)
+  const unsigned long long seed = fs.seed + static_cast<unsigned long long>(static_cast<unsigned>(fs.index[1])) *
+                                                0x9E3779B97F4A7C15ull;
+  const float* cf = fs.coef + static_cast<long long>(idx) * 8;
+  const long long g = static_cast<long long>(b) * per_sample + i;
+  const float x = fs.x[g];
+  const bool ddpm = fs.kind == 1;
+  float nz = 0.f;
+  if (!(ddpm && idx == 0))
+    nz = fs.noise ? fs.noise[g] : philox_normal(seed, fs.sample0 + b, static_cast<uint32_t>(i), idx, 0);
+  nz = __fmul_rn(nz, fs.temperature);
+  float xp;
+  if (ddpm) {
+    const float x0 = __fsub_rn(__fmul_rn(cf[0], x), __fmul_rn(cf[1], e));
+    const float mean = __fadd_rn(__fmul_rn(cf[2], x0), __fmul_rn(cf[3], x));
+    xp = __fadd_rn(mean, __fmul_rn(cf[4], nz));
+  } else {
+    const float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(cf[0], e)), cf[1]);
+    const float dir = __fmul_rn(cf[3], e);
+    xp = __fadd_rn(__fadd_rn(__fmul_rn(cf[2], x0), dir), __fmul_rn(cf[4], nz));
+  }
+  if (fs.orig) {
+    float nk = 0.f;
+    if (!(ddpm && idx == 0))
+      nk = fs.noise_kn ? fs.noise_kn[g] : philox_normal(seed, fs.sample0 + b, static_cast<uint32_t>(i), idx, 1);
+    const float xk = __fadd_rn(__fmul_rn(cf[5], fs.orig[g]), __fmul_rn(cf[6], nk));
+    const float m = fs.mask[g];
+    xp = __fadd_rn(__fmul_rn(xk, m), __fmul_rn(xp, __fsub_rn(1.0f, m)));
+  }
+  fs.x[g] = xp;
+  if (fs.eps_out) fs.eps_out[g] = e;
+}
+
+__global__ void __launch_bounds__(256) step_from_eps_kernel(const FusedStep fs, const float* __restrict__ eps,
+                                                            int B, long long per_sample) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= B * per_sample) return;
+  fused_step_apply(fs, static_cast<int>(i / per_sample), per_sample, i % per_sample, eps[i]);
+}
+void launch_step_from_eps(const FusedStep& fs, const float* eps, int B, long long per_sample, cudaStream_t s) {
+  const long long n = B * per_sample;
+  step_from_eps_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(fs, eps, B, per_sample);
+}
+__global__ void step_advance_kernel(int* index, long long* t, const long long* __restrict__ t_table, int B) {
+  const int idx = max(*index - 1, 0);
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) t[b] = t_table[idx];
+  if (threadIdx.x == 0) *index = idx;
+}
+void launch_step_advance(int* index, long long* t, const long long* t_table, int B, cudaStream_t s) {
+  step_advance_kernel<<<1, 256, 0, s>>>(index, t, t_table, B);
+}
+__global__ void fill_normal_kernel(float* __restrict__ out, long long n_samples, long long per_sample,
+                                   unsigned long long seed, long long sample0, int index, int which) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n_samples * per_sample) return;
+  out[i] = philox_normal(seed, sample0 + i / per_sample, static_cast<uint32_t>(i % per_sample), index, which);
+}
+void launch_fill_normal(float* out, long long n_samples, long long per_sample, unsigned long long seed,
+                        long long sample0, int index, int which, cudaStream_t s) {
+  const long long n = n_samples * per_sample;
+  fill_normal_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(out, n_samples, per_sample, seed,
+                                                                            sample0, index, which);
+}
+__global__ void gather_rows_kernel(const long long* __restrict__ t, const float* __restrict__ table,
+                                   float* __restrict__ dst, int n_rows, int width) {
+  const int b = blockIdx.y;
+  long long r = t[b];
+  r = r < 0 ? 0 : (r >= n_rows ? n_rows - 1 : r);
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < width; i += gridDim.x * 256)
+    dst[static_cast<long long>(b) * width + i] = table[r * width + i];
+}
+void launch_gather_rows(const long long* t, const float* table, float* dst, int B, int n_rows, int width,
+                        cudaStream_t s) {
+  dim3 grid((width + 255) / 256, B);
+  gather_rows_kernel<<<grid, 256, 0, s>>>(t, table, dst, n_rows, width);
+}
+
+// ------------------------------------------------------------------------------------------------
 // conv_out: GN-apply + SiLU + conv3x3 (C -> Cout<=4) -> NCHW.  16x16 pixel tile + halo in smem.
 // ------------------------------------------------------------------------------------------------
 constexpr int CO_T = 16;
@@ -866,13 +978,15 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__
 // (pitch 68 floats).
 constexpr int CO2_ROWS = 16, CO2_PITCH = 68, CO2_PW = 130;
 constexpr int CO2_SMEM = (128 * CO2_PITCH + 3 * 9 * 2 * CO2_PW + 2 * 9 * 64 + 128) * 4;
+template <bool FUSE>
 __global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict__ h,
                                                         const double* __restrict__ stats,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ bias,
-                                                        float* __restrict__ out, int H, int W) {
+                                                        float* __restrict__ out, int H, int W,
+                                                        const FusedStep fs) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm[];
@@ -969,24 +1083,36 @@ __global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict_
         for (int kx = 0; kx < 3; ++kx)
           sum += part[((sl * 9 + ky * 3 + kx) * 2 + co) * CO2_PW + x + kx];
       }
-      out[((static_cast<long long>(b) * 2 + co) * H + y) * W + x] = sum;
+      if constexpr (FUSE) {
+        // eps never leaves the SM: x_t -> x_{t-1} right here (north_star: "fused into the last kernel")
+        fused_step_apply(fs, b, 2ll * H * W, (static_cast<long long>(co) * H + y) * W + x, sum);
+      } else {
+        out[((static_cast<long long>(b) * 2 + co) * H + y) * W + x] = sum;
+      }
     }
   }
 }
 
 void launch_conv_out(const float* h, const double* stats, const float* gamma, const float* beta,
                      float eps, const float* w, const float* bias, float* out, int B, int H, int W,
-                     int C, int Cout, cudaStream_t s) {
+                     int C, int Cout, cudaStream_t s, const FusedStep* fs) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_out2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CO2_SMEM);
+    cudaFuncSetAttribute(conv_out2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CO2_SMEM);
+    cudaFuncSetAttribute(conv_out2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CO2_SMEM);
     attr_set = true;
   }
   static const bool slow = std::getenv("PF_CONV_SLOW") != nullptr;
+  const bool fuse = fs && fs->kind != 0;
   if (!slow && C == 64 && Cout == 2 && W <= 128) {
     dim3 grid((H + CO2_ROWS - 1) / CO2_ROWS, B);
-    launch_pdl(conv_out2_kernel, grid, dim3(256), CO2_SMEM, s, h, stats, gamma, beta, eps, w, bias, out, H, W);
+    FusedStep f{};
+    if (fuse) f = *fs;
+    if (fuse)
+      launch_pdl(conv_out2_kernel<true>, grid, dim3(256), CO2_SMEM, s, h, stats, gamma, beta, eps, w, bias, out, H, W, f);
+    else
+      launch_pdl(conv_out2_kernel<false>, grid, dim3(256), CO2_SMEM, s, h, stats, gamma, beta, eps, w, bias, out, H, W, f);
     return;
   }
   const size_t smem = (static_cast<size_t>(CO_T + 2) * (CO_T + 2) * (C + 4) +

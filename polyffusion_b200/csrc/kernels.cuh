@@ -71,10 +71,48 @@ void launch_small_linear(const float* in, long long ld_in, const float* W, const
                          float* out, long long ld_out, int B, int N, int K, int out_act,
                          cudaStream_t s, int groups = 1);
 
-// GroupNorm-apply + SiLU + conv3x3 (C -> Cout small) -> NCHW out (unet.py:145-149)
+// Reverse-diffusion step applied to eps where it is produced (the last kernel of the UNet evaluation),
+// driven entirely by device-side state so that a whole sampling step replays as one CUDA graph:
+//   index : device int32[2]: [0] row of `coef` for this replay (DDPM: the step; DDIM: the schedule index),
+//           [1] run nonce folded into the Philox key (seed + nonce * 0x9E3779B97F4A7C15)
+//   coef  : [n_index][8] = c0..c4 (meaning as in StepArgs), kn_a, kn_b, unused
+//   x     : x_t in, x_{t-1} out (in place; NCHW like eps)
+//   noise / noise_kn : injected N(0,1) tensors, or null -> Philox4x32-10 normals keyed by
+//           (seed, global sample index = sample0 + b, element, index, stream) -- independent of how the
+//           batch is sharded over ranks
+//   orig / mask : RePaint known region (null -> plain step)
+// DDPM adds no noise and re-noises the known region with zero noise at index 0 (sampler_sdf.py:152-153,
+// 322-324).  Arithmetic and rounding order are those of step_ddpm_kernel / step_ddim_kernel.
+struct FusedStep {
+  int kind;  // 0 none, 1 DDPM (sampler_sdf.py:121-171, 322-336), 2 DDIM (sampler_ddim.py:233-272, 355-359)
+  const int* index;
+  const float* coef;
+  float* x;
+  float* eps_out;  // optional copy of eps
+  const float* noise;
+  const float* noise_kn;
+  const float* orig;
+  const float* mask;
+  float temperature;
+  unsigned long long seed;
+  long long sample0;
+};
+
+// GroupNorm-apply + SiLU + conv3x3 (C -> Cout small) -> NCHW out (unet.py:145-149); with fs (kind != 0)
+// the reverse step is applied in the same kernel and `out` is not written
 void launch_conv_out(const float* h, const double* stats, const float* gamma, const float* beta,
                      float eps, const float* w, const float* bias, float* out, int B, int H, int W,
-                     int C, int Cout, cudaStream_t s);
+                     int C, int Cout, cudaStream_t s, const FusedStep* fs = nullptr);
+// the same step from an eps tensor [B, per_sample] (fallback for shapes without the fused conv kernel)
+void launch_step_from_eps(const FusedStep& fs, const float* eps, int B, long long per_sample, cudaStream_t s);
+// index = max(index - 1, 0); t[b] = t_table[index]  (end of a fused step)
+void launch_step_advance(int* index, long long* t, const long long* t_table, int B, cudaStream_t s);
+// out[b, i] = Philox normal (same generator as FusedStep): N(0,1) keyed by (seed, sample0 + b, i, index, which)
+void launch_fill_normal(float* out, long long n_samples, long long per_sample, unsigned long long seed,
+                        long long sample0, int index, int which, cudaStream_t s);
+// dst[b, :] = table[clamp(t[b], 0, n_rows - 1), :]   (time-embedding LUT gather)
+void launch_gather_rows(const long long* t, const float* table, float* dst, int B, int n_rows, int width,
+                        cudaStream_t s);
 
 // condition encoders: one GRU step, and TextureEncoder.cnn (conv (4,12)/(4,1) + ReLU + maxpool (1,4))
 void launch_gru_cell(const float* gi, long long gi_ld, const float* gh, const float* h, float* h_out,

@@ -72,7 +72,7 @@ struct BlockSpec {
 
 enum OpKind {
   OP_GEMM, OP_CONV_IN, OP_GN_STATS, OP_GN_FINALIZE, OP_ACT_SPLIT, OP_LN_SPLIT, OP_GEGLU, OP_SOFTMAX,
-  OP_TIME_SIN, OP_SMALL_LINEAR, OP_CONV_OUT, OP_MEMSET, OP_ATTN
+  OP_TIME_SIN, OP_SMALL_LINEAR, OP_CONV_OUT, OP_MEMSET, OP_ATTN, OP_GATHER_ROWS
 };
 enum ExtSlot { EXT_NONE = 0, EXT_X, EXT_T, EXT_COND, EXT_OUT };
 
@@ -87,6 +87,7 @@ struct Op {
   void* o[2] = {nullptr, nullptr};
   long long i[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float f = 0.f;
+  bool cond_only = false; // depends on `cond` alone (cross-attention vectors): once per sampling loop
   int lane = -1;          // -1: whole batch on the caller's stream; 0 / 1: half-batch lane (see Builder)
   long long ext_off = 0;  // element offset into the external tensor (lane 1 starts half a batch in)
 };
@@ -97,6 +98,7 @@ struct Plan {
   size_t bytes = 0;
   std::vector<Op> ops;
   bool has_lanes = false;
+  bool lut = false;  // built against the time-embedding LUT (pf_unet_enable_time_lut)
 };
 
 }  // namespace pf
@@ -120,6 +122,11 @@ struct pf_unet {
   bool packing = false;
   // second stream + fork/join events for the half-batch lanes (created lazily, never destroyed while
   // the handle lives; events are only ordering markers, timing disabled)
+  // [n_steps][emb_total] table of the per-ResBlock embedding projections for t = 0 .. n_steps - 1
+  // (pf_unet_enable_time_lut): a forward then gathers one row per sample instead of evaluating the
+  // sinusoid, the 2-layer MLP and the 22 projections
+  float* time_lut = nullptr;
+  int time_lut_rows = 0;
   cudaStream_t side_stream = nullptr;
   std::vector<cudaEvent_t> lane_events;
   size_t lane_event_next = 0;
@@ -1059,29 +1066,11 @@ struct Builder {
     return y;
   }
 
-  // ---------------------------------------------------------------- whole forward
-  void build(int H, int Wd) {
+  // sinusoid -> time_embed MLP -> the concatenated emb projections of every ResBlock, for the B timesteps
+  // of the external t tensor; returns [B, emb_total]
+  const float* emit_time_embedding() {
     const pf_unet_cfg& c = m->cfg;
     const int d_temb = c.channels * 4;
-    // GroupNorm accumulator pool: sized by a generous bound, zeroed once per forward
-    {
-      size_t doubles = 0;
-      auto count_block = [&](const BlockSpec& b) {
-        for (auto& l : b.layers) {
-          if (l.kind == Layer::RES) doubles += static_cast<size_t>(B) * (2 * l.cout) * 2;
-          else doubles += static_cast<size_t>(B) * l.cout * 2;
-        }
-      };
-      for (auto& b : m->input_blocks) count_block(b);
-      count_block(m->middle);
-      for (auto& b : m->output_blocks) count_block(b);
-      gn_pool_doubles = doubles;
-      gn_pool = alloc<double>(doubles);
-      Op& op = push(OP_MEMSET);
-      op.o[0] = gn_pool;
-      op.i[0] = static_cast<long long>(doubles * sizeof(double));
-    }
-    // ---- time embedding (unet.py:64-68, 151-169, 182) and all ResBlock emb projections
     float* sinus = alloc<float>(static_cast<size_t>(B) * c.channels);
     {
       Op& op = push(OP_TIME_SIN);
@@ -1115,7 +1104,43 @@ struct Builder {
       const float* bcat = Fcat(m, "emb_all.bias", bn_, &cb);
       float* ea = alloc<float>(static_cast<size_t>(B) * m->emb_total);
       small_linear(temb, d_temb, wcat, bcat, ea, m->emb_total, m->emb_total, d_temb, 0);
+      return ea;
+    }
+  }
+
+  // ---------------------------------------------------------------- whole forward
+  void build(int H, int Wd) {
+    const pf_unet_cfg& c = m->cfg;
+    // GroupNorm accumulator pool: sized by a generous bound, zeroed once per forward
+    {
+      size_t doubles = 0;
+      auto count_block = [&](const BlockSpec& b) {
+        for (auto& l : b.layers) {
+          if (l.kind == Layer::RES) doubles += static_cast<size_t>(B) * (2 * l.cout) * 2;
+          else doubles += static_cast<size_t>(B) * l.cout * 2;
+        }
+      };
+      for (auto& b : m->input_blocks) count_block(b);
+      count_block(m->middle);
+      for (auto& b : m->output_blocks) count_block(b);
+      gn_pool_doubles = doubles;
+      gn_pool = alloc<double>(doubles);
+      Op& op = push(OP_MEMSET);
+      op.o[0] = gn_pool;
+      op.i[0] = static_cast<long long>(doubles * sizeof(double));
+    }
+    // ---- time embedding (unet.py:64-68, 151-169, 182) and all ResBlock emb projections
+    if (m->time_lut && !m->packing) {
+      float* ea = alloc<float>(static_cast<size_t>(B) * m->emb_total);
+      Op& op = push(OP_GATHER_ROWS);
+      op.ext = EXT_T;
+      op.p[1] = m->time_lut;
+      op.o[0] = ea;
+      op.i[0] = B; op.i[1] = m->time_lut_rows; op.i[2] = m->emb_total;
       emb_all = ea;
+      plan->lut = true;
+    } else {
+      emb_all = emit_time_embedding();
     }
     // ---- cross-attention value vectors for n_cond == 1
     {
@@ -1146,14 +1171,17 @@ struct Builder {
         const int nv = ng * d_attn;
         float* cvall = alloc<float>(static_cast<size_t>(B) * nv);
         small_linear(nullptr, c.d_cond, wv, nullptr, cvall, nv, nv, c.d_cond, 0, EXT_COND);
+        plan->ops.back().cond_only = true;
         // softmax over a single key == 1: attn2(.) == to_out(to_v(cond)) for every token;
         // cross_cv[b, g] = Wout2_g . v_g[b] + bout2_g + bout1_g is added in the attn1 out-projection
         // epilogue of transformer g (all groups in ONE launch)
         float* cv = alloc<float>(static_cast<size_t>(B) * nv);
         small_linear(cvall, nv, wo, bo, cv, nv, d_attn, d_attn, 0, EXT_NONE, ng);
+        plan->ops.back().cond_only = true;
         cross_cv = cv;
         cross_cv_ld = nv;
-        afree(cvall);
+        // cvall is NOT returned to the arena: with a hoisted cond prologue (pf_unet_prepare_cond) its
+        // region must not be handed to a later op of the per-step part
       }
     }
     // ---- blocks
@@ -1214,8 +1242,13 @@ struct Builder {
       PF_CHECK(c.out_channels <= 4, "out_channels > 4 unsupported by the final conv kernel");
       PF_CHECK(xf.C % 32 == 0, "final GroupNorm: channels %d not divisible by 32", xf.C);
       const double* st = stats_of(xf);
+      // eps scratch of this (lane's) samples: only the generic conv_out kernel needs it when the step
+      // epilogue is fused (the 64 -> 2 fast path applies the step in registers)
+      float* eps_tmp = alloc<float>(static_cast<size_t>(B) * c.out_channels * H * Wd);
       Op& op = push(OP_CONV_OUT);
       op.ext = EXT_OUT;
+      op.o[1] = eps_tmp;
+      op.i[5] = lane == 1 ? B : 0;  // first sample of this lane (Philox sample index, x offset)
       op.ext_off = ext_lane_off(static_cast<long long>(c.out_channels) * H * Wd);
       op.p[0] = xf.p; op.p[1] = st; op.p[2] = F(m, "out.0.weight"); op.p[3] = F(m, "out.2.weight");
       op.p[4] = F(m, "out.2.bias"); op.p[5] = F(m, "out.0.bias");
@@ -1398,8 +1431,11 @@ static cudaEvent_t next_lane_event(pf_unet* m) {
 // the handle's side stream, forked / joined with events (legal under stream capture: the side stream
 // joins the capture at the fork and returns to the origin stream at the join).  With `events` (the
 // profiled run) everything is serialised on the caller's stream so that per-launch times add up.
+// ops_mode: 0 = every op, 1 = skip the cond-only prologue (already run by pf_unet_prepare_cond for this
+// cond), 2 = ONLY the cond-only prologue.  fs (optional): reverse-diffusion step fused into the last kernel.
 static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, const float* cond,
-                     float* out, cudaStream_t main_stream, std::vector<cudaEvent_t>* events = nullptr) {
+                     float* out, cudaStream_t main_stream, std::vector<cudaEvent_t>* events = nullptr,
+                     const FusedStep* fs = nullptr, int ops_mode = 0) {
   size_t opi = 0;
   static const bool lanes_serial = std::getenv("PF_LANES_SERIAL") != nullptr;
   const bool use_side = plan.has_lanes && !events && !lanes_serial;
@@ -1415,6 +1451,7 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
   };
   for (Op& op : plan.ops) {
     if (events) PF_CUDA(cudaEventRecord((*events)[opi++], main_stream));
+    if ((ops_mode == 1 && op.cond_only) || (ops_mode == 2 && !op.cond_only)) continue;
     cudaStream_t s = main_stream;
     if (use_side) {
       if (op.lane >= 0 && !forked) {
@@ -1477,12 +1514,33 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
                             static_cast<float*>(op.o[0]), op.i[1], (int)op.i[2], (int)op.i[3],
                             (int)op.i[4], (int)op.i[5], s, op.i[6] > 0 ? (int)op.i[6] : 1);
         break;
-      case OP_CONV_OUT:
+      case OP_GATHER_ROWS:
+        launch_gather_rows(reinterpret_cast<const long long*>(t), static_cast<const float*>(op.p[1]),
+                           static_cast<float*>(op.o[0]), (int)op.i[0], (int)op.i[1], (int)op.i[2], s);
+        break;
+      case OP_CONV_OUT: {
+        const int Bl = (int)op.i[0], Hh = (int)op.i[1], Ww = (int)op.i[2], Cc = (int)op.i[3], Co = (int)op.i[4];
+        FusedStep f{};
+        if (fs && fs->kind != 0) {
+          // this (lane's) slice of the sampler state
+          f = *fs;
+          const long long off = op.i[5] * static_cast<long long>(Co) * Hh * Ww;
+          f.x += off;
+          if (f.eps_out) f.eps_out += off;
+          if (f.noise) f.noise += off;
+          if (f.noise_kn) f.noise_kn += off;
+          if (f.orig) { f.orig += off; f.mask += off; }
+          f.sample0 += op.i[5];
+        }
+        const bool fast = Cc == 64 && Co == 2 && Ww <= 128;
+        float* dst = f.kind == 0 ? out + op.ext_off : static_cast<float*>(op.o[1]);
         launch_conv_out(static_cast<const float*>(op.p[0]), static_cast<const double*>(op.p[1]),
                         static_cast<const float*>(op.p[2]), static_cast<const float*>(op.p[5]), op.f,
-                        static_cast<const float*>(op.p[3]), static_cast<const float*>(op.p[4]),
-                        out + op.ext_off, (int)op.i[0], (int)op.i[1], (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
+                        static_cast<const float*>(op.p[3]), static_cast<const float*>(op.p[4]), dst, Bl, Hh, Ww, Cc,
+                        Co, s, f.kind != 0 && fast ? &f : nullptr);
+        if (f.kind != 0 && !fast) launch_step_from_eps(f, dst, Bl, static_cast<long long>(Co) * Hh * Ww, s);
         break;
+      }
     }
   }
   join();
@@ -1574,6 +1632,8 @@ int pf_unet_finalize(pf_unet* h, pf_stream stream) {
     h->fvecs.clear();
     h->plans.clear();
     h->last_plan = nullptr;
+    h->time_lut = nullptr;  // (freed with `owned` above; the sampler re-enables it after a weight update)
+    h->time_lut_rows = 0;
     h->pack_stream = static_cast<cudaStream_t>(stream);
     h->packing = true;
     struct Reset {
@@ -1621,6 +1681,85 @@ int pf_unet_forward(pf_unet* h, const float* x, const int64_t* time_steps, const
   });
 }
 
+static FusedStep to_fused(const pf_fused_step* a) {
+  FusedStep f{};
+  f.kind = a->kind; f.index = a->index; f.coef = a->coef; f.x = a->x; f.eps_out = a->eps_out;
+  f.noise = a->noise; f.noise_kn = a->noise_kn; f.orig = a->orig; f.mask = a->mask;
+  f.temperature = a->temperature; f.seed = a->seed; f.sample0 = a->sample0;
+  return f;
+}
+
+int pf_unet_forward_step(pf_unet* h, const float* x_in, int64_t* time_steps, const float* cond, int32_t batch,
+                         int32_t n_cond, int32_t height, int32_t width, const pf_fused_step* step,
+                         void* workspace, size_t workspace_bytes, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(h && h->finalized, "model not finalized");
+    PF_CHECK(x_in && time_steps && cond && workspace && step, "null argument");
+    PF_CHECK((step->kind == 1 || step->kind == 2) && step->index && step->coef && step->t_table && step->x,
+             "bad fused step arguments");
+    PF_CHECK(!step->orig || step->mask, "RePaint needs a mask (sampler_sdf.py:310)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Plan* plan = get_plan(h, cond, batch, n_cond, height, width, workspace, workspace_bytes);
+    const FusedStep f = to_fused(step);
+    run_plan(h, *plan, x_in, time_steps, cond, nullptr, s, nullptr, &f, (step->flags & 1) ? 1 : 0);
+    launch_step_advance(step->index, reinterpret_cast<long long*>(time_steps),
+                        reinterpret_cast<const long long*>(step->t_table), batch, s);
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
+int pf_unet_prepare_cond(pf_unet* h, const float* cond, int32_t batch, int32_t n_cond, int32_t height,
+                         int32_t width, void* workspace, size_t workspace_bytes, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(h && h->finalized && cond && workspace, "bad arguments");
+    Plan* plan = get_plan(h, cond, batch, n_cond, height, width, workspace, workspace_bytes);
+    run_plan(h, *plan, nullptr, nullptr, cond, nullptr, static_cast<cudaStream_t>(stream), nullptr, nullptr, 2);
+  });
+}
+
+int pf_unet_enable_time_lut(pf_unet* h, int32_t n_steps, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(h && h->finalized && n_steps > 0 && n_steps <= (1 << 20), "bad arguments");
+    if (h->time_lut && h->time_lut_rows == n_steps) return;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // evaluate the plan's own time-embedding ops (sinusoid, 2-layer MLP, the concatenated ResBlock
+    // projections) for t = 0 .. n_steps - 1 as a batch: the table rows are bit-identical to what a forward
+    // computes for that t
+    h->time_lut = nullptr;
+    h->plans.clear();
+    h->last_plan = nullptr;
+    const size_t ws_bytes = static_cast<size_t>(n_steps) * (h->cfg.channels * 9 + h->emb_total) * sizeof(float) + (1 << 20);
+    char* ws = nullptr;
+    long long* tt = nullptr;
+    PF_CUDA(cudaMalloc(&ws, ws_bytes));
+    PF_CUDA(cudaMalloc(&tt, n_steps * sizeof(long long)));
+    std::vector<long long> host(n_steps);
+    for (int i = 0; i < n_steps; ++i) host[i] = i;
+    PF_CUDA(cudaMemcpyAsync(tt, host.data(), n_steps * sizeof(long long), cudaMemcpyHostToDevice, s));
+    Plan plan;
+    Builder b(h, &plan, ws, false, n_steps, 1);
+    const float* ea = b.emit_time_embedding();
+    run_plan(h, plan, nullptr, reinterpret_cast<const int64_t*>(tt), nullptr, nullptr, s);
+    float* lut = static_cast<float*>(dev_alloc(h, static_cast<size_t>(n_steps) * h->emb_total * sizeof(float)));
+    PF_CUDA(cudaMemcpyAsync(lut, ea, static_cast<size_t>(n_steps) * h->emb_total * sizeof(float),
+                            cudaMemcpyDeviceToDevice, s));
+    PF_CUDA(cudaStreamSynchronize(s));
+    cudaFree(ws);
+    cudaFree(tt);
+    h->time_lut = lut;
+    h->time_lut_rows = n_steps;
+  });
+}
+
+int pf_fill_normal(float* out, int64_t n_samples, int64_t per_sample, uint64_t seed, int64_t sample0,
+                   int32_t index, int32_t which, pf_stream stream) {
+  return guarded([&] {
+    PF_CHECK(out && n_samples > 0 && per_sample > 0 && per_sample < (1ll << 32), "bad arguments");
+    launch_fill_normal(out, n_samples, per_sample, seed, sample0, index, which, static_cast<cudaStream_t>(stream));
+    PF_CUDA(cudaGetLastError());
+  });
+}
+
 int pf_unet_forward_profiled(pf_unet* h, const float* x, const int64_t* time_steps, const float* cond,
                              int32_t batch, int32_t n_cond, int32_t height, int32_t width, float* out,
                              void* workspace, size_t workspace_bytes, pf_stream stream,
@@ -1658,7 +1797,7 @@ static Plan* get_plan(pf_unet* h, const float* cond, int32_t batch, int32_t n_co
     Plan* plan = nullptr;
     for (auto& p : h->plans)
       if (p->B == batch && p->n_cond == n_cond && p->H == height && p->W == width &&
-          p->workspace == workspace) {
+          p->workspace == workspace && p->lut == (h->time_lut != nullptr)) {
         plan = p.get();
         break;
       }
@@ -1702,7 +1841,7 @@ int pf_unet_op_desc(pf_unet* h, int32_t i, char* buf, int32_t len) {
     const Op& op = h->last_plan->ops[i];
     static const char* names[] = {"gemm", "conv_in", "gn_stats", "gn_finalize", "act_split", "ln_split",
                                   "geglu", "softmax", "time_sin", "small_linear", "conv_out", "memset",
-                                  "attn"};
+                                  "attn", "gather_rows"};
     if (op.kind == OP_GEMM) {
       const GemmParams& g = op.g;
       int k = 0;

@@ -30,6 +30,8 @@ class UNetEngine:
         self._workspaces: "OrderedDict[Tuple[int, int, int, int], torch.Tensor]" = OrderedDict()
         self._graphs: "OrderedDict[Tuple[int, int, int, int], tuple]" = OrderedDict()
         self._cache_entries = max(1, int(os.environ.get("PF_ENGINE_CACHE", "4")))
+        self._lut_rows = 0
+        self.generation = 0
         # replay each (batch, n_cond, H, W) evaluation as a CUDA graph (measured ~3 % faster than the
         # 261 individual launches); PF_CUDA_GRAPH=0 disables it
         self.use_graph = os.environ.get("PF_CUDA_GRAPH", "1") != "0"
@@ -67,6 +69,7 @@ class UNetEngine:
         while len(self._workspaces) > self._cache_entries:
             old, _ = self._workspaces.popitem(last=False)
             self._graphs.pop(old, None)
+            self.generation += 1  # a workspace went away: graphs captured over it are stale
 
     def sync_weights(self, device: torch.device, force: bool = False) -> None:
         """(Re)pack the module's current parameters into the library."""
@@ -96,6 +99,8 @@ class UNetEngine:
             check(lib().pf_unet_finalize(self.handle, current_stream()))
         del keep
         self._stamp = stamp
+        self._lut_rows = 0  # pf_unet_finalize dropped the time-embedding table
+        self.generation += 1  # plans were rebuilt: graphs captured by callers (FusedLoop) are stale
         self._workspaces.clear()
         self._graphs.clear()
 
@@ -162,9 +167,9 @@ class UNetEngine:
         out.copy_(os_)
         return out
 
-    def _forward_eager(self, key, x, t, cond, out, profile):
+    def workspace(self, key, dev):
+        """(tensor, 1024-aligned base address, usable bytes) of the plan workspace for (B, n_cond, H, W)."""
         B, n_cond, H, W = key
-        dev = x.device
         with torch.cuda.device(dev):
             ws = self._workspaces.get(key)
             if ws is not None:
@@ -176,7 +181,24 @@ class UNetEngine:
                 ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
                 self._workspaces[key] = ws
                 self._touch(key)
-            base = (ws.data_ptr() + 1023) // 1024 * 1024
+        base = (ws.data_ptr() + 1023) // 1024 * 1024
+        return ws, base, ws.numel() - (base - ws.data_ptr())
+
+    def enable_time_lut(self, n_steps: int) -> None:
+        """Tabulate the time-embedding path for t = 0 .. n_steps-1 (pf_unet_enable_time_lut); samplers call
+        this, a bare UNetModel.forward keeps evaluating it.  Plans and graphs are rebuilt against the table."""
+        if getattr(self, "_lut_rows", 0) == n_steps:
+            return
+        check(lib().pf_unet_enable_time_lut(self.handle, int(n_steps), current_stream()))
+        self._lut_rows = n_steps
+        self.generation += 1
+        self._graphs.clear()
+
+    def _forward_eager(self, key, x, t, cond, out, profile):
+        B, n_cond, H, W = key
+        dev = x.device
+        with torch.cuda.device(dev):
+            ws, base, _ = self.workspace(key, dev)
             if out is None:
                 out = torch.empty((B, self.cfg["out_channels"], H, W), dtype=torch.float32, device=dev)
             if profile is None:

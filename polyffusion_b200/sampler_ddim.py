@@ -13,6 +13,9 @@ from typing import List, Optional
 import numpy as np
 import torch
 
+import os
+
+from polyffusion_b200._loop import FusedLoop
 from polyffusion_b200._step import fused_q_sample, fused_step
 from polyffusion_b200.stable_diffusion.latent_diffusion import LatentDiffusion
 from polyffusion_b200.stable_diffusion.sampler import DiffusionSampler
@@ -53,6 +56,42 @@ class DDIMSampler(DiffusionSampler):
                 "qa": self.ddim_alpha_sqrt.tolist(),
                 "qb": self.ddim_sqrt_one_minus_alpha.tolist(),
             }
+        # whole-step graph loop / noise source: as in SDFSampler (sampler_sdf.py, _loop.py)
+        self.fused_loop = os.environ.get("PF_FUSED_LOOP", "1") != "0"
+        self.noise = os.environ.get("PF_NOISE", "torch")
+        self.seed = 0
+        self.sample0 = 0
+        h = self._h
+        self._loop = FusedLoop(self.model.eps_model, 2,
+                               [(h["c0"][i], h["c1"][i], h["c2"][i], h["c3"][i], h["c4"][i], h["qa"][i], h["qb"][i])
+                                for i in range(len(self.time_steps))], [int(v) for v in self.time_steps])
+
+    def _can_fuse(self, x, uncond_scale, uncond_cond, cond_concat):
+        from polyffusion_b200.stable_diffusion.model.unet import UNetModel
+
+        guided = uncond_cond is not None and uncond_scale not in (0.0, 1.0)
+        return (self.fused_loop and x.is_cuda and not guided and cond_concat is None
+                and isinstance(self.model.eps_model, UNetModel) and self.model.first_stage_model is None)
+
+    def _run_fused(self, x, cond, start, n, *, orig, mask, orig_noise, temperature, repeat_noise, uncond_scale,
+                   uncond_cond):
+        if uncond_cond is not None and uncond_scale == 0.0:
+            cond = uncond_cond
+        shape = tuple(x.shape)
+        sigma = self._h["c4"]
+
+        def draw(index):
+            # reference order inside a step: step noise if sigma != 0 (sampler_ddim.py:255-262), then the
+            # known-region noise of q_sample when no orig_noise was given (:293-294)
+            nz = None
+            if sigma[index] != 0.0:
+                nz = torch.randn((1, *shape[1:]) if repeat_noise else shape, device=x.device)
+            nk = torch.randn_like(orig) if (orig is not None and orig_noise is None) else None
+            return nk, nz
+
+        return self._loop.run(x, cond, start, n, orig=orig, mask=mask, noise_mode=self.noise,
+                              fixed_noise_kn=orig_noise if orig is not None else None, temperature=temperature,
+                              seed=self.seed, sample0=self.sample0, draw=draw)
 
     def _coefs(self, index: int):
         h = self._h
@@ -90,11 +129,35 @@ class DDIMSampler(DiffusionSampler):
         bs = shape[0]
         x = x_last if x_last is not None else torch.randn(shape, device=device)
         time_steps = np.flip(self.time_steps)[t_start:]
+        if len(time_steps) and self._can_fuse(x, uncond_scale, uncond_cond, None):
+            return self._run_fused(x, cond, len(time_steps) - 1, len(time_steps), orig=None, mask=None,
+                                   orig_noise=None, temperature=temperature, repeat_noise=repeat_noise,
+                                   uncond_scale=uncond_scale, uncond_cond=uncond_cond)
         for i, step in enumerate(time_steps):
             index = len(time_steps) - i - 1
             ts = x.new_full((bs,), int(step), dtype=torch.long)
             x, _, _ = self._step(x, cond, ts, index, repeat_noise=repeat_noise, temperature=temperature,
                                  uncond_scale=uncond_scale, uncond_cond=uncond_cond, want_aux=False)
+        return x
+
+    @torch.no_grad()
+    def advance(self, x: torch.Tensor, cond: torch.Tensor, start_index: int, n_steps: int, *,
+                orig: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+                orig_noise: Optional[torch.Tensor] = None, uncond_scale: float = 1.0,
+                uncond_cond: Optional[torch.Tensor] = None, cond_concat=None):
+        """``n_steps`` consecutive iterations of the sample / paint loop body (sampler_ddim.py:145-163,
+        343-359) starting at schedule index ``start_index``."""
+        n_steps = min(int(n_steps), int(start_index) + 1)
+        if self._can_fuse(x, uncond_scale, uncond_cond, cond_concat):
+            return self._run_fused(x, cond, int(start_index), n_steps, orig=orig, mask=mask, orig_noise=orig_noise,
+                                   temperature=1.0, repeat_noise=False, uncond_scale=uncond_scale,
+                                   uncond_cond=uncond_cond)
+        bs = x.shape[0]
+        for index in range(int(start_index), int(start_index) - n_steps, -1):
+            ts = x.new_full((bs,), int(self.time_steps[index]), dtype=torch.long)
+            x, _, _ = self._step(x, cond, ts, index, uncond_scale=uncond_scale, uncond_cond=uncond_cond,
+                                 cond_concat=cond_concat, orig=orig, mask=mask, orig_noise=orig_noise,
+                                 want_aux=False)
         return x
 
     @torch.no_grad()
@@ -131,6 +194,10 @@ class DDIMSampler(DiffusionSampler):
         q_sample(orig, index, orig_noise) (the *current* index, fixed noise)."""
         bs = x.shape[0]
         time_steps = np.flip(self.time_steps[: t_start + 1])
+        if repaint_n == 1 and self._can_fuse(x, uncond_scale, uncond_cond, cond_concat):
+            return self._run_fused(x, cond, len(time_steps) - 1, len(time_steps), orig=orig, mask=mask,
+                                   orig_noise=orig_noise, temperature=1.0, repeat_noise=False,
+                                   uncond_scale=uncond_scale, uncond_cond=uncond_cond)
         for i, step in enumerate(time_steps):
             index = len(time_steps) - i - 1
             ts = x.new_full((bs,), int(step), dtype=torch.long)

@@ -13,6 +13,12 @@ signatures as sampler_sdf.py:37-350.  What differs is where the work happens:
 
 Random numbers are drawn with ``torch.randn`` in the reference's order (known-region noise first,
 then step noise), so a seeded run consumes the generator exactly like the reference does.
+
+``sample`` / ``paint`` loops without classifier-free guidance run as replays of ONE CUDA graph per step
+(``_loop.FusedLoop``: UNet + in-kernel step + device-side step counter; the time embedding comes from a
+table, the cross-attention vectors are computed once per loop).  ``sampler.noise = "philox"`` switches
+those loops to in-kernel Philox noise keyed by the global sample index (``sampler.seed``,
+``sampler.sample0``), which makes a batch sharded over ranks reproduce the single-GPU result.
 """
 from __future__ import annotations
 
@@ -21,6 +27,9 @@ from typing import List, Optional
 import numpy as np
 import torch
 
+import os
+
+from polyffusion_b200._loop import FusedLoop
 from polyffusion_b200._step import fused_q_sample, fused_step
 from polyffusion_b200.stable_diffusion.latent_diffusion import LatentDiffusion
 from polyffusion_b200.stable_diffusion.sampler import DiffusionSampler
@@ -58,6 +67,39 @@ class SDFSampler(DiffusionSampler):
                 "rp_a": ((1 - beta) ** 0.5).tolist(),
                 "rp_b": beta.tolist(),
             }
+        # whole-step graph loop (see module docstring); PF_FUSED_LOOP=0 keeps the per-step launches
+        self.fused_loop = os.environ.get("PF_FUSED_LOOP", "1") != "0"
+        self.noise = os.environ.get("PF_NOISE", "torch")  # "torch" (reference order) | "philox" (in-kernel)
+        self.seed = 0
+        self.sample0 = 0  # global index of this shard's first sample (Philox mode)
+        h = self._h
+        self._loop = FusedLoop(self.model.eps_model, 1,
+                               [(h["c0"][i], h["c1"][i], h["c2"][i], h["c3"][i], h["c4"][i], h["qa"][i], h["qb"][i])
+                                for i in range(self.n_steps)], list(range(self.n_steps)))
+
+    def _can_fuse(self, x, uncond_scale, uncond_cond, cond_concat, repaint_n=1):
+        from polyffusion_b200.stable_diffusion.model.unet import UNetModel
+
+        guided = uncond_cond is not None and uncond_scale not in (0.0, 1.0)
+        return (self.fused_loop and x.is_cuda and not guided and cond_concat is None and repaint_n == 1
+                and isinstance(self.model.eps_model, UNetModel) and self.model.first_stage_model is None)
+
+    def _run_fused(self, x, cond, start, n, *, orig, mask, temperature, repeat_noise, uncond_scale, uncond_cond):
+        if uncond_cond is not None and uncond_scale == 0.0:
+            cond = uncond_cond  # sampler/__init__.py:66-67
+        shape = tuple(x.shape)
+
+        def draw(step):
+            # the reference's order: known-region noise (sampler_sdf.py:318), then the step noise (:157-160)
+            nk = torch.randn_like(orig, device=orig.device) if (orig is not None and step > 0) else None
+            if step == 0:
+                return nk, None
+            if repeat_noise:
+                return nk, torch.randn((1, *shape[1:]), device=x.device)
+            return nk, torch.randn(shape, device=x.device)
+
+        return self._loop.run(x, cond, start, n, orig=orig, mask=mask, noise_mode=self.noise,
+                              temperature=temperature, seed=self.seed, sample0=self.sample0, draw=draw)
 
     def _coefs(self, step: int):
         h = self._h
@@ -104,10 +146,33 @@ class SDFSampler(DiffusionSampler):
         bs = shape[0]
         x = x_last if x_last is not None else torch.randn(shape, device=cond.device)
         time_steps = np.flip(self.time_steps)[t_start:]
+        if len(time_steps) and self._can_fuse(x, uncond_scale, uncond_cond, None):
+            return self._run_fused(x, cond, int(time_steps[0]), len(time_steps), orig=None, mask=None,
+                                   temperature=temperature, repeat_noise=repeat_noise,
+                                   uncond_scale=uncond_scale, uncond_cond=uncond_cond)
         for step in time_steps:
             ts = x.new_full((bs,), int(step), dtype=torch.long)
             x, _, _ = self._step(x, cond, ts, step, repeat_noise=repeat_noise, temperature=temperature,
                                  uncond_scale=uncond_scale, uncond_cond=uncond_cond, want_aux=False)
+        return x
+
+    @torch.no_grad()
+    def advance(self, x: torch.Tensor, cond: torch.Tensor, start_step: int, n_steps: int, *,
+                orig: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+                uncond_scale: float = 1.0, uncond_cond: Optional[torch.Tensor] = None, cond_concat=None):
+        """``n_steps`` consecutive iterations of ``paint``'s loop body (sampler_sdf.py:292-341) starting at
+        ``start_step``: ``paint(x, cond, t_start, ...) == advance(x, cond, t_start, t_start + 1, ...)``.
+        Lets a caller (bench.py, a progress UI) run the chain in slices."""
+        n_steps = min(int(n_steps), int(start_step) + 1)
+        if self._can_fuse(x, uncond_scale, uncond_cond, cond_concat):
+            return self._run_fused(x, cond, int(start_step), n_steps, orig=orig, mask=mask, temperature=1.0,
+                                   repeat_noise=False, uncond_scale=uncond_scale, uncond_cond=uncond_cond)
+        bs = x.shape[0]
+        for step in range(int(start_step), int(start_step) - n_steps, -1):
+            ts = x.new_full((bs,), step, dtype=torch.long)
+            noise_kn = torch.randn_like(orig, device=orig.device) if (orig is not None and step > 0) else None
+            x, _, _ = self._step(x, cond, ts, step, uncond_scale=uncond_scale, uncond_cond=uncond_cond,
+                                 cond_concat=cond_concat, orig=orig, mask=mask, noise_kn=noise_kn, want_aux=False)
         return x
 
     @torch.no_grad()
@@ -121,6 +186,10 @@ class SDFSampler(DiffusionSampler):
         bs = x.shape[0]
         time_steps = np.flip(self.time_steps[: t_start + 1])
         print(f"RePainting: sampling steps = {repaint_n}")
+        if self._can_fuse(x, uncond_scale, uncond_cond, cond_concat, repaint_n):
+            assert orig is None or mask is not None
+            return self._run_fused(x, cond, int(t_start), len(time_steps), orig=orig, mask=mask, temperature=1.0,
+                                   repeat_noise=False, uncond_scale=uncond_scale, uncond_cond=uncond_cond)
         for step in time_steps:
             step = int(step)
             ts = x.new_full((bs,), step, dtype=torch.long)

@@ -185,7 +185,11 @@ def test_ddpm_temperature_and_repeat_noise_vs_oracle(rig):
             t = torch.full((2,), step, dtype=torch.long, device="cuda")
             got, got_x0, _ = s.p_sample(x.cuda(), cond.cuda(), t, step, repeat_noise=rep, temperature=temp)
         _assert_close(got, want, f"p_sample step={step} temperature={temp} repeat_noise={rep}")
-        _assert_close(got_x0, want_x0, f"x0 step={step}")
+        # x0 = sqrt(1/abar) x - sqrt(1/abar - 1) eps (sampler_sdf.py:137-141): an eps error is multiplied
+        # by sqrt(1/abar - 1) (14.6 at step 999), so the UNet tolerance is scaled by that factor
+        amp = max(1.0, float(tb["sqrt_recip_m1_ab"][step]))
+        d = (got_x0.cpu() - want_x0).abs()
+        assert bool((d <= amp * ATOL + RTOL * want_x0.abs()).all()), f"x0 step={step}: max abs err {d.max().item()}"
 
 
 def test_cond_concat_vs_oracle():
