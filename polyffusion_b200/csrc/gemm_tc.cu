@@ -82,9 +82,14 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, long long 
 // instead of 12 bf16 MMAs; the epilogue returns acc0 + 2^-17 acc1.  CPU emulation of the scheme on the
 // whole UNet (tools/experiments/precision_emul.py): max |err| 5.9e-5, rms 9.3e-6 against the fp32
 // reference (bf16x3: 2.0e-5 / 3.9e-6; tolerance 1e-4 + 1e-3 |ref|).
-template <int BN, bool TWO, int MODE, bool STATS, bool STACK, bool HALO, bool F8 = false>
+// NACC = accumulator stages in TMEM.  2 everywhere (the epilogue of tile i overlaps the main loop of tile
+// i + 1) except the BN = 256 f16f8 kernels: their two accumulators of 256 columns fill the 512 TMEM columns,
+// so the epilogue is exposed (a few % of a K >= 2304 tile) in exchange for reading every A tile from shared
+// memory once per 256 output columns -- the f16f8 kernels at BN = 128 are shared-memory-bandwidth bound
+// (fill 94 B/clk + UMMA operand reads 96 B/clk against 128 B/clk).
+template <int BN, bool TWO, int MODE, bool STATS, bool STACK, bool HALO, bool F8 = false, int NACC = 2>
 __device__ __forceinline__ void gemm_body(const GemmParams& p) {
-  static_assert(!F8 || (!STACK && BN <= 128), "f16f8 needs two accumulators of BN columns, double buffered");
+  static_assert(!F8 || (!STACK && NACC * 2 * BN <= 512), "f16f8 needs two accumulators of BN columns per stage");
   static_assert(!STACK || (TWO && BN <= 128), "stacked B operand needs cta_group::2 and 4*BN <= 512 TMEM columns");
   static_assert(!HALO || TWO, "halo stages are implemented for cta_group::2 only");
   extern __shared__ uint8_t smem_raw[];
@@ -104,7 +109,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   constexpr uint32_t IDESC_2N = umma_idesc_bf16_m256(STACK ? 2 * BN : BN);
   constexpr int ACC_COLS = (STACK || F8) ? 2 * BN : BN;  // TMEM columns of one accumulator stage
   constexpr int LOMUL = F8 ? 2 : 1;  // the fp8 tensors are byte maps: 2 bytes per (channel) element
-  constexpr int TMEM_COLS = 2 * ACC_COLS;        // 128 / 256 / 512: power of two >= 32
+  constexpr int TMEM_COLS = NACC * ACC_COLS;     // 128 / 256 / 512: power of two >= 32
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0);
   // tile walk: 1-CTA: tile t of this CTA; 2-CTA: pair-tile t of this cluster, my m-tile = 2*pair + rank
@@ -214,8 +219,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       int it = 0;
       int lt = 0;  // local tile counter
       for (long long t = wid; t < total_tiles; t += wstride, ++lt) {
-        const int as = lt & 1;
-        const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
+        const int as = lt % NACC;
+        const uint32_t aph = static_cast<uint32_t>(lt / NACC) & 1u;
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1u);
         tc_fence_after();
         const uint32_t acc = tmem_base + static_cast<uint32_t>(as * ACC_COLS);
@@ -294,8 +299,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     int lt = 0;
     for (long long t = wid; t < total_tiles; t += wstride, ++lt) {
       const TileCoord tc = decode_tile(p, t, BN, TWO ? static_cast<int>(rank) : -1);
-      const int as = lt & 1;
-      const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
+      const int as = lt % NACC;
+      const uint32_t aph = static_cast<uint32_t>(lt / NACC) & 1u;
       const long long m0 = static_cast<long long>(tc.tile) * GEMM_BM + q * 32;  // first row of this warp
       const long long zoff = tc.zb * p.out_zb + tc.zh * p.out_zh;
       if ((MODE == OUT_F32 || MODE == OUT_SPLIT || MODE == OUT_SPLIT8) && p.resid != nullptr) {
@@ -581,6 +586,12 @@ template <int BN, int MODE, bool STATS>
 __global__ void __launch_bounds__(GEMM_LB_THREADS, 1) gemm_tcf_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, false, MODE, STATS, false, false, true>(p);
 }
+// BN = 256, one accumulator stage (see NACC above)
+template <int MODE, bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
+    gemm_tc2f256_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<256, true, MODE, STATS, false, false, true, 1>(p);
+}
 
 typedef void (*GemmKernel)(GemmParams);
 
@@ -644,8 +655,20 @@ static GemmKernel pick_f8(int kind, int v) {
   }
 }
 
+static GemmKernel pick_f8_256(int kind, int v) {
+  if (kind != 4) return nullptr;
+  switch (v) {
+    case 0: return gemm_tc2f256_kernel<OUT_F32, false>;
+    case 1: return gemm_tc2f256_kernel<OUT_F32, true>;
+    case 2: return gemm_tc2f256_kernel<OUT_SPLIT, false>;
+    case 5: return gemm_tc2f256_kernel<OUT_SPLIT8, false>;
+    default: return nullptr;
+  }
+}
+
 static GemmKernel pick_kernel(int bn, int kind, int v) {
-  if (kind >= 4) return bn == 64 ? pick_f8<64>(kind, v) : bn == 128 ? pick_f8<128>(kind, v) : nullptr;
+  if (kind >= 4)
+    return bn == 64 ? pick_f8<64>(kind, v) : bn == 128 ? pick_f8<128>(kind, v) : bn == 256 ? pick_f8_256(kind, v) : nullptr;
   if (kind == 3) {  // halo stages: BN = 64, fp32 output (with / without statistics)
     if (bn != 64 || v > 1) return nullptr;
     return v == 1 ? gemm_tc2h_kernel<64, true> : gemm_tc2h_kernel<64, false>;

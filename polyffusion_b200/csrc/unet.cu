@@ -604,7 +604,14 @@ struct Builder {
   // f32_out = false: the caller will select a split output mode (no halo kernel for those)
   Op& conv_gemm(const ASrc& a0, PackedW& w0, const ASrc* a1, PackedW* w1, int Ho, int Wo, int Cout,
                 int row0 = 0, int bn_override = 0, bool f32_out = true) {
-    const int bn = bn_override ? bn_override : choose_bn(Cout);
+    // f16f8 convolutions with Cout % 256 == 0 can use 256-wide tiles (one accumulator stage, gemm_tc.cu
+    // NACC).  Measured on B200 (profiles/r3e_*): 600 vs 638 TF/s at K = 4608, 406 vs 420 at 16 x 16 -- the
+    // exposed epilogue costs more than the halved A operand reads buy, so PF_F8_BN256=1 is opt-in
+    static const bool f8_bn256 = std::getenv("PF_F8_BN256") && std::atoi(std::getenv("PF_F8_BN256")) != 0;
+    const bool pairs = (B * ((Wo / choose_box_w(Wo)) * (Ho / (128 / choose_box_w(Wo))))) % 2 == 0;
+    const int bn = bn_override ? bn_override
+                               : (a0.f8 && f8_bn256 && pairs && Cout % 256 == 0 && std::getenv("PF_GEMM_1CTA") == nullptr)
+                                     ? 256 : choose_bn(Cout);
     const int box_w = choose_box_w(Wo);
     PF_CHECK(128 % box_w == 0 && Wo % box_w == 0, "unsupported width %d", Wo);
     const int box_h = 128 / box_w;
@@ -623,7 +630,7 @@ struct Builder {
     static const int stack_sel = std::getenv("PF_GEMM_STACK") ? std::atoi(std::getenv("PF_GEMM_STACK")) : -1;
     g.f8 = a0.f8 ? 1 : 0;
     PF_CHECK(!a1 || a1->f8 == a0.f8, "GEMM segments with different operand formats");
-    PF_CHECK(!g.f8 || bn <= 128, "f16f8 GEMM: BN=%d > 128", bn);
+    PF_CHECK(!g.f8 || bn <= 128 || two, "f16f8 GEMM: BN=%d needs CTA pairs", bn);
     g.stack = (!g.f8 && two && bn <= 128 && (stack_sel < 0 || stack_sel == bn)) ? 1 : 0;
     // halo stages for the N = 64 3x3 convolutions at 128 x 128 (tile = one image row): A bytes
     // through L2 drop 2.95x (these launches were L2 -> SM bandwidth bound).  PF_GEMM_HALO=0 disables.
