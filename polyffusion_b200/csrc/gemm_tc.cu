@@ -87,8 +87,22 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, long long 
 // so the epilogue is exposed (a few % of a K >= 2304 tile) in exchange for reading every A tile from shared
 // memory once per 256 output columns -- the f16f8 kernels at BN = 128 are shared-memory-bandwidth bound
 // (fill 94 B/clk + UMMA operand reads 96 B/clk against 128 B/clk).
-template <int BN, bool TWO, int MODE, bool STATS, bool STACK, bool HALO, bool F8 = false, int NACC = 2>
+//
+// RAW (cta_group::2, 512 threads): segments flagged GemmSeg::raw take their A operand straight from fp32
+// NHWC tensors.  TMA drops the fp32 tile (128 pixels x 64 channels = 32 KB, exactly the size of the stage's
+// hi + lo A tiles) into the stage; four conversion warps (12..15) pull it into registers, apply the optional
+// per-row (LayerNorm) and per-(image, channel) (GroupNorm / LayerNorm affine) maps and SiLU, and write the
+// K-major SWIZZLE_128B operand tiles back IN PLACE (split-bf16 or f16f8), fence them into the async proxy and
+// arrive on the leader's conv_full barrier.  For a 1x1 consumer
+// every element is converted once per N tile, so the plain split of the ResBlock skip-conv input, the
+// GroupNorm'd operand of proj_in and the LayerNorm'd operands of the q/k/v and GeGLU projections are never
+// written to or read from HBM.
+// STATS: 0 none, 1 per-(image, column) GroupNorm sums (fp64 atomics), 2 per-row sums (fp32 atomics, LayerNorm
+// statistics for a RAW consumer).
+template <int BN, bool TWO, int MODE, int STATS, bool STACK, bool HALO, bool F8 = false, int NACC = 2,
+          bool RAW = false>
 __device__ __forceinline__ void gemm_body(const GemmParams& p) {
+  static_assert(!RAW || TWO, "raw segments are implemented for cta_group::2 only");
   static_assert(!F8 || (!STACK && NACC * 2 * BN <= 512), "f16f8 needs two accumulators of BN columns per stage");
   static_assert(!STACK || (TWO && BN <= 128), "stacked B operand needs cta_group::2 and 4*BN <= 512 TMEM columns");
   static_assert(!HALO || TWO, "halo stages are implemented for cta_group::2 only");
@@ -97,6 +111,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t raw_full[RAW ? MAX_STAGES : 1];   // fp32 tile landed (this CTA)
+  __shared__ __align__(8) uint64_t conv_full[RAW ? MAX_STAGES : 1];  // operand tiles written (both CTAs -> leader)
   __shared__ uint32_t tmem_base_s;
 
   constexpr int A_BYTES = GEMM_BM * 128;
@@ -129,6 +145,10 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     for (int i = 0; i < nstages; ++i) {
       mbar_init(smem_u32(&full_bar[i]), 1);
       mbar_init(smem_u32(&empty_bar[i]), 1);
+      if (RAW) {
+        mbar_init(smem_u32(&raw_full[i]), 1);
+        mbar_init(smem_u32(&conv_full[i]), 8);  // one arrive per conversion warp of both CTAs
+      }
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
@@ -160,6 +180,12 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   pdl_wait();     // operands / residual / statistics of earlier kernels are complete from here on
   pdl_trigger();  // let the next kernel's CTAs start their prologue during our tail
 
+  // RAW kernels run 512 threads = 4 warpgroups (WG0: TMA, MMA, two idle warps; WG1-2: epilogue; WG3: conversion)
+  // at 128 registers each.  Re-dividing the register file with setmaxnreg (56 / 168 / 120) made things worse:
+  // ptxas 12.9 compiled the WHOLE kernel under the smallest of the three limits (4.4 KB of spills against
+  // 0.2 KB at a flat 128).
+  constexpr int EPI_WARP0 = RAW ? 4 : 2;  // first epilogue warp (8 of them: warp & 3 = TMEM lane quarter)
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
@@ -188,7 +214,19 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
               mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1u);
               const uint32_t fb = smem_u32(&full_bar[stage]);
               const uint32_t sa = ring + stage * STAGE_BYTES;
-              if (TWO) {
+              if (RAW && sg.raw) {
+                // fp32 tile -> this CTA's A area (own barrier, converted in place by warps 12..15); the B
+                // tiles complete on the leader's barrier as usual
+                const uint32_t rf = smem_u32(&raw_full[stage]);
+                const int ch = acol + kb * GEMM_BK;
+                const bool second = ch >= sg.raw_c0;
+                mbar_expect_tx(rf, 2u * A_BYTES);
+                tma_load_4d(sa, second ? &sg.a_lo : &sg.a_hi, rf, second ? ch - sg.raw_c0 : ch, ax, ay, ai);
+                if (leader) mbar_expect_tx(fb, 2u * 2u * B_BYTES);
+                const uint32_t sb = sa + 2 * A_SLOT;
+                tma2_load_2d(sb, &sg.b_hi, fb, bcol + kb * GEMM_BK, br);
+                tma2_load_2d(sb + B_BYTES, &sg.b_lo, fb, (bcol + kb * GEMM_BK) * LOMUL, br);
+              } else if (TWO) {
                 // both CTAs' loads complete on the LEADER's barrier, which expects both halves
                 if (leader) mbar_expect_tx(fb, 2 * tx);
                 tma2_load_4d(sa, &sg.a_hi, fb, acol + kb * GEMM_BK, ax, ay, ai);
@@ -218,6 +256,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     if (leader && elect_one()) {
       int it = 0;
       int lt = 0;  // local tile counter
+      uint32_t conv_bits = 0;  // phase parity of conv_full[] per stage
       for (long long t = wid; t < total_tiles; t += wstride, ++lt) {
         const int as = lt % NACC;
         const uint32_t aph = static_cast<uint32_t>(lt / NACC) & 1u;
@@ -233,6 +272,10 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
             const int stage = it % nstages;
             const uint32_t ph = static_cast<uint32_t>(it / nstages) & 1u;
             mbar_wait(smem_u32(&full_bar[stage]), ph);
+            if (RAW && sg.raw) {
+              mbar_wait(smem_u32(&conv_full[stage]), (conv_bits >> stage) & 1u);
+              conv_bits ^= 1u << stage;
+            }
             tc_fence_after();
             const uint32_t sa = ring + stage * STAGE_BYTES;
 #pragma unroll
@@ -279,7 +322,144 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         else umma_commit(smem_u32(&tmem_full_bar[as]));
       }
     }
-  } else {
+  } else if (RAW && warp >= 12) {
+    // ------------------------------------------------------------------ operand conversion (4 warps)
+    // thread = channels [4j, 4j + 4) and [32 + 4j, 32 + 4j + 4) of rows r0, r0 + 16, ... of every raw k-block:
+    // a quarter-warp reads 128 contiguous bytes per request (no bank conflicts) and the two 8-byte halves of a
+    // 16-byte operand chunk come from neighbouring lanes.  The code is specialised per transform kind and kept
+    // small (the conversion warps were instruction-fetch bound with one general 36 KB loop body).
+    const int tt = threadIdx.x - 384;  // 0..127
+    const int j = tt & 7;
+    // rows r0 + 16 i.  A warp takes rows w, w + 4, w + 8, w + 12: their swizzle phases (row & 7) pair up as
+    // {w, w + 4}, so the four 64-byte row pieces of one STS.64 cover all 32 banks twice (2 wavefronts, the
+    // minimum); with four consecutive rows per warp they fell on the same 16 banks (2-way conflicts)
+    const int r0 = ((tt >> 3) & 3) * 4 + (tt >> 5);
+    uint8_t* gsm = smem_raw + (ring - smem_u32(smem_raw));
+    uint32_t raw_bits = 0;
+    int it = 0;
+    for (long long t = wid; t < total_tiles; t += wstride) {
+      const TileCoord tc = decode_tile(p, t, BN, static_cast<int>(rank));
+      for (int s = 0; s < p.nseg; ++s) {
+        const GemmSeg& sg = p.seg[s];
+        const int nst = (HALO ? sg.ngroups : sg.ntaps) * sg.kb_per_tap;
+        if (!sg.raw) {
+          it += nst;
+          continue;
+        }
+        const bool rown = sg.raw_rowstats != nullptr;
+        const bool aff = sg.raw_scale != nullptr;
+        float rmul[8], radd[8];
+        if (rown) {
+          const float inv = 1.0f / static_cast<float>(sg.raw_rowlen);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long m = static_cast<long long>(tc.tile) * GEMM_BM + i * 16 + r0;
+            const float2 st = __ldcg(reinterpret_cast<const float2*>(sg.raw_rowstats) + m);
+            const float mean = st.x * inv;
+            const float var = fmaxf(fmaf(-mean, mean, st.y * inv), 0.f);
+            const float rstd = rsqrtf(var + sg.raw_eps);
+            rmul[i] = rstd;
+            radd[i] = -mean * rstd;
+          }
+        }
+        // per-channel scale / shift of the first k-block (the next one is fetched while this one is converted)
+        const float* scp = aff ? sg.raw_scale + static_cast<long long>(tc.img) * sg.raw_ld + sg.a_col0 + j * 4 : nullptr;
+        const float* shp = aff ? sg.raw_shift + static_cast<long long>(tc.img) * sg.raw_ld + sg.a_col0 + j * 4 : nullptr;
+        float4 sca, scb, sha, shb;
+        if (aff) {
+          sca = __ldg(reinterpret_cast<const float4*>(scp));
+          scb = __ldg(reinterpret_cast<const float4*>(scp + 32));
+          sha = __ldg(reinterpret_cast<const float4*>(shp));
+          shb = __ldg(reinterpret_cast<const float4*>(shp + 32));
+        }
+        for (int kb = 0; kb < nst; ++kb, ++it) {
+          const int stage = it % nstages;
+          mbar_wait(smem_u32(&raw_full[stage]), (raw_bits >> stage) & 1u);
+          raw_bits ^= 1u << stage;
+          uint8_t* a0 = gsm + stage * STAGE_BYTES;
+          float4 va[8], vb[8];
+          if (p.raw_dbg & 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) va[i] = vb[i] = make_float4(1.f, 2.f, 3.f, 4.f);
+          } else
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4* rp = reinterpret_cast<const float4*>(a0 + (i * 16 + r0) * 256 + j * 16);
+            va[i] = rp[0];
+            vb[i] = rp[8];
+          }
+          // every thread has its fp32 values in registers before anyone overwrites the tile
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          float4 nsa, nsb, nha, nhb;
+          if (aff && kb + 1 < nst) {
+            nsa = __ldg(reinterpret_cast<const float4*>(scp + (kb + 1) * GEMM_BK));
+            nsb = __ldg(reinterpret_cast<const float4*>(scp + (kb + 1) * GEMM_BK + 32));
+            nha = __ldg(reinterpret_cast<const float4*>(shp + (kb + 1) * GEMM_BK));
+            nhb = __ldg(reinterpret_cast<const float4*>(shp + (kb + 1) * GEMM_BK + 32));
+          }
+          if (rown) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              va[i].x = fmaf(va[i].x, rmul[i], radd[i]); va[i].y = fmaf(va[i].y, rmul[i], radd[i]);
+              va[i].z = fmaf(va[i].z, rmul[i], radd[i]); va[i].w = fmaf(va[i].w, rmul[i], radd[i]);
+              vb[i].x = fmaf(vb[i].x, rmul[i], radd[i]); vb[i].y = fmaf(vb[i].y, rmul[i], radd[i]);
+              vb[i].z = fmaf(vb[i].z, rmul[i], radd[i]); vb[i].w = fmaf(vb[i].w, rmul[i], radd[i]);
+            }
+          }
+          if (aff) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              va[i].x = fmaf(va[i].x, sca.x, sha.x); va[i].y = fmaf(va[i].y, sca.y, sha.y);
+              va[i].z = fmaf(va[i].z, sca.z, sha.z); va[i].w = fmaf(va[i].w, sca.w, sha.w);
+              vb[i].x = fmaf(vb[i].x, scb.x, shb.x); vb[i].y = fmaf(vb[i].y, scb.y, shb.y);
+              vb[i].z = fmaf(vb[i].z, scb.z, shb.z); vb[i].w = fmaf(vb[i].w, scb.w, shb.w);
+            }
+          }
+          if (!(p.raw_dbg & 1))
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int prow = i * 16 + r0;
+            const int x7 = prow & 7;
+            uint8_t* hrow = a0 + prow * 128 + (j & 1) * 8;
+            if constexpr (F8) {
+              uint2 ha, hb;
+              uint32_t h8a, l8a, h8b, l8b;
+              split_f8x4(va[i].x, va[i].y, va[i].z, va[i].w, 1.f, F8_ACT_LO_SCALE, ha, h8a, l8a);
+              split_f8x4(vb[i].x, vb[i].y, vb[i].z, vb[i].w, 1.f, F8_ACT_LO_SCALE, hb, h8b, l8b);
+              *reinterpret_cast<uint2*>(hrow + (((j >> 1) ^ x7) << 4)) = ha;
+              *reinterpret_cast<uint2*>(hrow + (((4 + (j >> 1)) ^ x7) << 4)) = hb;
+              uint8_t* lrow = a0 + A_SLOT + prow * 128 + (j & 3) * 4;
+              *reinterpret_cast<uint32_t*>(lrow + (((j >> 2) ^ x7) << 4)) = h8a;
+              *reinterpret_cast<uint32_t*>(lrow + (((2 + (j >> 2)) ^ x7) << 4)) = h8b;
+              *reinterpret_cast<uint32_t*>(lrow + (((4 + (j >> 2)) ^ x7) << 4)) = l8a;
+              *reinterpret_cast<uint32_t*>(lrow + (((6 + (j >> 2)) ^ x7) << 4)) = l8b;
+            } else {
+              uint2 ha, la, hb, lb;
+              split2(va[i].x, va[i].y, ha.x, la.x);
+              split2(va[i].z, va[i].w, ha.y, la.y);
+              split2(vb[i].x, vb[i].y, hb.x, lb.x);
+              split2(vb[i].z, vb[i].w, hb.y, lb.y);
+              const int oa = ((j >> 1) ^ x7) << 4, ob = ((4 + (j >> 1)) ^ x7) << 4;
+              *reinterpret_cast<uint2*>(hrow + oa) = ha;
+              *reinterpret_cast<uint2*>(hrow + ob) = hb;
+              *reinterpret_cast<uint2*>(hrow + A_SLOT + oa) = la;
+              *reinterpret_cast<uint2*>(hrow + A_SLOT + ob) = lb;
+            }
+          }
+          // generic-proxy writes -> visible to the tensor core (async proxy) of THIS SM, which is the one that
+          // reads this CTA's A tile (the leader only issues the instruction).  The .shared::cta form is a
+          // FENCE.VIEW.ASYNC; the unqualified fence and a cluster-scope release arrive both lower to
+          // MEMBAR.ALL.GPU, which cost ~0.7 us per k-block here.
+          if (!(p.raw_dbg & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(smem_u32(&conv_full[stage]));
+          if (aff) {
+            sca = nsa; scb = nsb; sha = nha; shb = nhb;
+          }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 8) {
     // ------------------------------------------------------------------ epilogue (8 warps)
     // TMEM -> registers (thread = output row) -> per-warp smem staging -> coalesced global stores:
     // in the store phase a quarter-warp (8 lanes x float4) covers one 128-byte row segment, so
@@ -289,12 +469,12 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     // per-channel sum / sum-of-squares of the stored values (GroupNorm statistics for the consumer)
     // are reduced in registers -> shuffles -> smem -> one fp64 atomicAdd per (tile, column).
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int ewarp = warp - 2;        // 0..7
+    const int ewarp = warp - EPI_WARP0;  // 0..7
     const int chalf = ewarp >> 2;      // which alternate chunks this warp takes
     uint8_t* epi_base = smem_raw + (ring - smem_u32(smem_raw)) + nstages * STAGE_BYTES;
     float* stg_all = reinterpret_cast<float*>(epi_base);
     float* stg = stg_all + ewarp * STG_FLOATS;
-    const int et = threadIdx.x - 64;   // 0..255 among epilogue threads
+    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255 among epilogue threads
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     int lt = 0;
     for (long long t = wid; t < total_tiles; t += wstride, ++lt) {
@@ -378,8 +558,13 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         const int ocol0 = geglu ? (tc.n0 / 2) : tc.n0;  // first output column
         const float* av = p.addvec ? p.addvec + static_cast<long long>(tc.img) * p.addvec_ld : nullptr;
         const bool has_res = (MODE == OUT_F32 || MODE == OUT_SPLIT || MODE == OUT_SPLIT8) && p.resid != nullptr;
-        float4 csum[STATS ? BN / 64 : 1], csq[STATS ? BN / 64 : 1];  // per-chunk column partial sums
-#pragma unroll(STATS ? BN / 64 : 1)
+        float4 csum[STATS == 1 ? BN / 64 : 1], csq[STATS == 1 ? BN / 64 : 1];  // per-chunk column partial sums
+        float rsum[STATS == 2 ? 8 : 1], rsq[STATS == 2 ? 8 : 1];               // per-row partial sums
+        if constexpr (STATS == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rsum[i] = rsq[i] = 0.f;
+        }
+#pragma unroll(STATS == 1 ? BN / 64 : 1)
         for (int ci = 0; ci < BN / 64; ++ci) {
           const int c = chalf * 32 + ci * 64;
           if (c >= ncols) break;
@@ -448,10 +633,14 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 o.x += rres[it].x; o.y += rres[it].y; o.z += rres[it].z; o.w += rres[it].w;
               }
               *reinterpret_cast<float4*>(p.out + zoff + m * p.ldc + tc.n0 + c + c4) = o;
-              if constexpr (STATS) {
+              if constexpr (STATS == 1) {
                 ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
                 ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y);
                 ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+              }
+              if constexpr (STATS == 2) {
+                rsum[it] += (o.x + o.y) + (o.z + o.w);
+                rsq[it] = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, rsq[it]))));
               }
             } else if constexpr (MODE == OUT_SPLIT8) {
               // f16f8 activation operand: h16 [m, ldc] fp16 + fp8 rows [m][ldc / 64][h8 x 64 | l8 x 64]
@@ -481,7 +670,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
               *reinterpret_cast<uint2*>(p.out_lo + off) = l;
             }
           }
-          if constexpr (STATS) {
+          if constexpr (STATS == 1) {
             // reduce over the 4 row-groups of the warp (lanes with equal lane&7)
 #pragma unroll
             for (int o = 8; o <= 16; o <<= 1) {
@@ -499,7 +688,27 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           }
           __syncwarp();
         }
-        if (STATS && lane < 8) {
+        if constexpr (STATS == 2) {
+          // a row's 32-column pieces sit in the 8 lanes of a quarter-warp: reduce, then one atomic pair per
+          // (row, warp, tile); the other column chunks / N tiles of the row add theirs
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 1; o <= 4; o <<= 1) {
+              rsum[i] += __shfl_xor_sync(0xffffffffu, rsum[i], o);
+              rsq[i] += __shfl_xor_sync(0xffffffffu, rsq[i], o);
+            }
+          }
+          if ((lane & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float* d = p.rowstats + (m0 + i * 4 + rsub) * 2;
+              atomicAdd(d, rsum[i]);
+              atomicAdd(d + 1, rsq[i]);
+            }
+          }
+        }
+        if (STATS == 1 && lane < 8) {
           // park the partials in this warp's (now idle) staging tile: [chunk][sum | sq][32 cols]
 #pragma unroll
           for (int ci = 0; ci < BN / 64; ++ci) {
@@ -515,7 +724,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         if (TWO) mbar_arrive_leader(smem_u32(&tmem_empty_bar[as]));
         else mbar_arrive(smem_u32(&tmem_empty_bar[as]));
       }
-      if constexpr (STATS) {
+      if constexpr (STATS == 1) {
         // flush this tile's column sums: [img][stats_ld][2] fp64
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et < BN) {
@@ -546,53 +755,76 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   }
 }
 
-template <int BN, int MODE, bool STATS>
+template <int BN, int MODE, int STATS>
 __global__ void __launch_bounds__(GEMM_LB_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, false, MODE, STATS, false, false>(p);
 }
 
-template <int BN, int MODE, bool STATS>
+template <int BN, int MODE, int STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, true, MODE, STATS, false, false>(p);
 }
 
 // cta_group::2 with the stacked [B_hi ; B_lo] operand (BN <= 128)
-template <int BN, int MODE, bool STATS>
+template <int BN, int MODE, int STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
     gemm_tc2s_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, true, MODE, STATS, true, false>(p);
 }
 
 // stacked B + halo stages (one 130-pixel A row serves the three dx taps); fp32 output only
-template <int BN, bool STATS>
+template <int BN, int STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
     gemm_tc2h_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, true, OUT_F32, STATS, true, true>(p);
 }
 
 // f16f8 operands (fp16 main product + e4m3 cross terms): cta_group::2, halo and single-CTA forms
-template <int BN, int MODE, bool STATS>
+template <int BN, int MODE, int STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
     gemm_tc2f_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, true, MODE, STATS, false, false, true>(p);
 }
-template <int BN, bool STATS>
+template <int BN, int STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
     gemm_tc2fh_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, true, OUT_F32, STATS, false, true, true>(p);
 }
-template <int BN, int MODE, bool STATS>
+template <int BN, int MODE, int STATS>
 __global__ void __launch_bounds__(GEMM_LB_THREADS, 1) gemm_tcf_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<BN, false, MODE, STATS, false, false, true>(p);
 }
 // BN = 256, one accumulator stage (see NACC above)
-template <int MODE, bool STATS>
+template <int MODE, int STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_LB_THREADS, 1)
     gemm_tc2f256_kernel(const __grid_constant__ GemmParams p) {
   gemm_body<256, true, MODE, STATS, false, false, true, 1>(p);
 }
 
+// RAW-segment kernels (512 threads: the conversion warps are warpgroup 3), only the shapes the UNet plan uses
+template <int BN, int MODE, int STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_RAW_THREADS, 1)
+    gemm_tc2f_raw_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, true, MODE, STATS, false, false, true, 2, true>(p);
+}
+template <int BN, int STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_RAW_THREADS, 1)
+    gemm_tc2fh_raw_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, true, OUT_F32, STATS, false, true, true, 2, true>(p);
+}
+template <int BN, int MODE, int STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_RAW_THREADS, 1)
+    gemm_tc2s_raw_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, true, MODE, STATS, true, false, false, 2, true>(p);
+}
+template <int BN, int MODE, int STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_RAW_THREADS, 1)
+    gemm_tc2_raw_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BN, true, MODE, STATS, false, false, false, 2, true>(p);
+}
+
+#ifndef PF_GEMM_NO_DISPATCH  // (register-allocation experiments instantiate single kernels: tools/)
 typedef void (*GemmKernel)(GemmParams);
 
 // variant index: 0 = fp32, 1 = fp32 + GroupNorm statistics, 2 = split, 3 = split transposed, 4 = GeGLU
@@ -606,6 +838,7 @@ static GemmKernel pick_variant(int v) {
       case 2: return gemm_tc2s_kernel<BN, OUT_SPLIT, false>;
       case 3: return gemm_tc2s_kernel<BN, OUT_SPLIT_T, false>;
       case 5: return gemm_tc2s_kernel<BN, OUT_SPLIT8, false>;
+      case 6: return gemm_tc2s_kernel<BN, OUT_F32, 2>;
       default: return gemm_tc2s_kernel<BN, OUT_GEGLU, false>;
     }
   } else if constexpr (KIND == 1) {
@@ -615,6 +848,7 @@ static GemmKernel pick_variant(int v) {
       case 2: return gemm_tc2_kernel<BN, OUT_SPLIT, false>;
       case 3: return gemm_tc2_kernel<BN, OUT_SPLIT_T, false>;
       case 5: return gemm_tc2_kernel<BN, OUT_SPLIT8, false>;
+      case 6: return gemm_tc2_kernel<BN, OUT_F32, 2>;
       default: return gemm_tc2_kernel<BN, OUT_GEGLU, false>;
     }
   } else {
@@ -624,6 +858,7 @@ static GemmKernel pick_variant(int v) {
       case 2: return gemm_tc_kernel<BN, OUT_SPLIT, false>;
       case 3: return gemm_tc_kernel<BN, OUT_SPLIT_T, false>;
       case 5: return gemm_tc_kernel<BN, OUT_SPLIT8, false>;
+      case 6: return gemm_tc_kernel<BN, OUT_F32, 2>;
       default: return gemm_tc_kernel<BN, OUT_GEGLU, false>;
     }
   }
@@ -666,7 +901,34 @@ static GemmKernel pick_f8_256(int kind, int v) {
   }
 }
 
-static GemmKernel pick_kernel(int bn, int kind, int v) {
+// kernels with RAW segments: kind 2 (stacked split-bf16, BN = 128: transformer linears), kind 1 (BN = 256:
+// GeGLU projection), kind 4 (f16f8, BN = 64 / 128) and kind 5 (f16f8 halo, BN = 64): ResBlock second conv + raw
+// 1x1 skip segment
+static GemmKernel pick_raw(int bn, int kind, int v) {
+  if (kind == 2 && bn == 128) {
+    switch (v) {
+      case 0: return gemm_tc2s_raw_kernel<128, OUT_F32, 0>;
+      case 6: return gemm_tc2s_raw_kernel<128, OUT_F32, 2>;
+      case 2: return gemm_tc2s_raw_kernel<128, OUT_SPLIT, 0>;
+      case 3: return gemm_tc2s_raw_kernel<128, OUT_SPLIT_T, 0>;
+      default: return nullptr;
+    }
+  }
+  if (kind == 1 && bn == 256) return v == 4 ? gemm_tc2_raw_kernel<256, OUT_GEGLU, 0> : nullptr;
+  if (kind == 5 && bn == 64) return v == 1 ? gemm_tc2fh_raw_kernel<64, 1> : v == 0 ? gemm_tc2fh_raw_kernel<64, 0> : nullptr;
+  if (kind == 4 && bn == 64) return v == 1 ? gemm_tc2f_raw_kernel<64, OUT_F32, 1> : nullptr;
+  if (kind == 4 && bn == 128) {
+    switch (v) {
+      case 1: return gemm_tc2f_raw_kernel<128, OUT_F32, 1>;
+      case 5: return gemm_tc2f_raw_kernel<128, OUT_SPLIT8, 0>;
+      default: return nullptr;
+    }
+  }
+  return nullptr;
+}
+
+static GemmKernel pick_kernel(int bn, int kind, int v, bool raw = false) {
+  if (raw) return pick_raw(bn, kind, v);
   if (kind >= 4)
     return bn == 64 ? pick_f8<64>(kind, v) : bn == 128 ? pick_f8<128>(kind, v) : bn == 256 ? pick_f8_256(kind, v) : nullptr;
   if (kind == 3) {  // halo stages: BN = 64, fp32 output (with / without statistics)
@@ -684,20 +946,38 @@ static GemmKernel pick_kernel(int bn, int kind, int v) {
 cudaError_t gemm_init_attrs() {
   for (int bn : {64, 128, 256})
     for (int kind = 0; kind < 7; ++kind)
-      for (int v = 0; v < 6; ++v) {
-        GemmKernel k = pick_kernel(bn, kind, v);
-        if (!k) continue;
-        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k),
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (e != cudaSuccess) return e;
-      }
+      for (int v = 0; v < 7; ++v)
+        for (int raw = 0; raw < 2; ++raw) {
+          GemmKernel k = pick_kernel(bn, kind, v, raw != 0);
+          if (!k) continue;
+          cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k),
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+          if (e != cudaSuccess) return e;
+        }
   return cudaSuccess;
+}
+
+static int gemm_kind(const GemmParams& p, int bn) {
+  return p.f8 ? (p.two_cta ? (p.halo ? 5 : 4) : 6)
+              : p.two_cta ? (p.halo ? 3 : (p.stack && bn <= 128) ? 2 : 1) : 0;
+}
+static int gemm_variant(const GemmParams& p) {
+  switch (p.mode) {
+    case OUT_F32: return p.stats ? 1 : p.rowstats ? 6 : 0;
+    case OUT_SPLIT: return 2;
+    case OUT_SPLIT_T: return 3;
+    case OUT_SPLIT8: return 5;
+    default: return 4;
+  }
+}
+bool gemm_kernel_available(const GemmParams& p, int bn) {
+  return pick_kernel(bn, gemm_kind(p, bn), gemm_variant(p), p.raw != 0) != nullptr;
 }
 
 cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t stream) {
   int v;
   switch (p.mode) {
-    case OUT_F32: v = p.stats ? 1 : 0; break;
+    case OUT_F32: v = p.stats ? 1 : p.rowstats ? 6 : 0; break;
     case OUT_SPLIT: v = 2; break;
     case OUT_SPLIT_T: v = 3; break;
     case OUT_SPLIT8: v = 5; break;
@@ -705,20 +985,24 @@ cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t 
   }
   const int kind = p.f8 ? (p.two_cta ? (p.halo ? 5 : 4) : 6)
                         : p.two_cta ? (p.halo ? 3 : (p.stack && bn <= 128) ? 2 : 1) : 0;
-  GemmKernel k = pick_kernel(bn, kind, v);
+  GemmKernel k = pick_kernel(bn, kind, v, p.raw != 0);
   if (!k) return cudaErrorInvalidValue;
+  if (p.raw && !p.two_cta) return cudaErrorInvalidValue;
+  const int nthreads = p.raw ? GEMM_RAW_THREADS : GEMM_THREADS;
   if (p.two_cta) {
     const int smem = p.nstages * (p.halo ? gemm_stage_bytes2_halo(bn) : gemm_stage_bytes2(bn)) + 1024 +
                      gemm_epilogue_smem_bytes(bn);
     const long long pairs = static_cast<long long>(p.n_tiles) * (p.m_tiles / 2) * p.z_count;
     const long long max_clusters = num_ctas / 2;
     const unsigned grid = 2u * static_cast<unsigned>(pairs < max_clusters ? pairs : max_clusters);
-    return launch_pdl(k, dim3(grid), dim3(GEMM_THREADS), smem, stream, p);
+    return launch_pdl(k, dim3(grid), dim3(nthreads), smem, stream, p);
   }
   const int smem = gemm_smem_bytes(bn, p.nstages) + gemm_epilogue_smem_bytes(bn);
   const long long total = static_cast<long long>(p.n_tiles) * p.m_tiles * p.z_count;
   const unsigned grid = static_cast<unsigned>(total < num_ctas ? total : num_ctas);
   return launch_pdl(k, dim3(grid), dim3(GEMM_THREADS), smem, stream, p);
 }
+
+#endif  // PF_GEMM_NO_DISPATCH
 
 }  // namespace pf

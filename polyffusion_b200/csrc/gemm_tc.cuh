@@ -23,6 +23,7 @@ constexpr int GEMM_THREADS = 320; // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int GEMM_MAX_TAPS = 12;
 constexpr int GEMM_HALO_ROWS = 130;            // halo stage: one image row of 128 pixels + 1 on each side
 constexpr int GEMM_HALO_A_SLOT = 17 * 1024;    // 130 x 128 B rounded up to the 1024-byte swizzle atom
+constexpr int GEMM_RAW_THREADS = 512;          // kernels with raw segments: warpgroup 3 = operand-conversion warps
 
 enum GemmOutMode : int {
   OUT_F32 = 0,        // fp32 row-major [m, ldc] (+ addvec[img, n] + resid[m, n])
@@ -46,6 +47,20 @@ struct alignas(64) GemmSeg {
   // halo kernels only: taps [g*gtaps, (g+1)*gtaps) share one A box of a_rows pixels (tap j starts j
   // rows in); other kernels ignore these (every tap is its own stage)
   int ngroups, gtaps, a_rows;
+  // RAW segment (1x1 taps only, kernels with conversion warps -- gemm_tc.cu): the A operand is formed INSIDE
+  // the GEMM from fp32 NHWC tensors.  a_hi / a_lo are then fp32 maps {C, W, H, N} (box 64 x box_w x box_h, no
+  // swizzle) of the first / second concatenated source; k-blocks below raw_c0 channels come from the first.
+  // v = ((x - mean_r) * rstd_r) * scale[img or 0][c] + shift[..][c], optional SiLU; mean_r / rstd_r from the
+  // per-row sums raw_rowstats[row][2] = (sum x, sum x^2) over raw_rowlen channels (LayerNorm) or 0 / 1 when
+  // raw_rowstats is null; scale / shift null = identity.  The stage's 32 KB A area receives the fp32 tile by
+  // TMA and is converted in place (registers in between) into the K-major SWIZZLE_128B operand tiles.
+  int raw, raw_c0, raw_silu, raw_rowlen;
+  const float* raw_scale;
+  const float* raw_shift;
+  const float* raw_rowstats;
+  long long raw_ld;   // scale / shift row stride per image (0: one vector for all images)
+  float raw_eps;
+  int pad1;
 };
 
 struct alignas(64) GemmParams {
@@ -67,11 +82,15 @@ struct alignas(64) GemmParams {
   long long addvec_ld, ldr;
   double* stats;        // OUT_F32 only: per-(image, column) sum / sum-of-squares [img][stats_ld][2]
   long long stats_ld;
+  float* rowstats;      // OUT_F32 only (optional): per-row (sum, sum of squares) of the stored values, fp32
+                        // atomics into zero-initialised [m][2] (LayerNorm statistics for a RAW consumer)
   int geglu_f;          // OUT_GEGLU: number of output features F (bias layout [x: F | gate: F])
   int two_cta;          // 1: cta_group::2 kernel (tile pairs; B maps have boxes of BN/2 rows)
   int stack;            // 1 (with two_cta, BN <= 128): stacked [B_hi ; B_lo] operand, 2 MMAs per K step
   int halo;             // 1 (with two_cta, BN = 64, box 128 x 1, OUT_F32): halo stages, see gemm_tc.cu
   int f8;               // 1: f16f8 operands (a_hi/b_hi = fp16 maps, a_lo/b_lo = byte maps of the fp8 rows)
+  int raw_dbg;          // (timing experiments only: skip parts of the conversion, results are garbage)
+  int raw;              // 1: at least one segment is RAW (512-thread kernel with conversion warps; two_cta only)
   // nearest-2x-upsample + conv3x3 evaluated as four 2x2 parity convolutions at LOW resolution:
   // OUT_F32 rows are scattered to pixel (2y + up_py, 2x + up_px) of the [img][2H][2W] output
   int up_mode, up_py, up_px;
@@ -91,5 +110,7 @@ inline int gemm_epilogue_smem_bytes(int /*bn*/) { return 8 * 32 * 32 * 4; }
 // persistent launch: min(#tiles, num_ctas) CTAs
 cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t stream);
 cudaError_t gemm_init_attrs();
+// whether a kernel exists for this (tile width, operand scheme, output mode, raw) combination
+bool gemm_kernel_available(const GemmParams& p, int bn);
 
 }  // namespace pf

@@ -41,6 +41,21 @@ CUtensorMap make_map_4d(const void* ptr, int C, int W, int H, int N, int box_w, 
   return m;
 }
 
+CUtensorMap make_map_4d_f32(const void* ptr, int C, int W, int H, int N, int box_w, int box_h) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fail("cuTensorMapEncodeTiled(4d f32 C=%d W=%d H=%d N=%d box=%dx%d) failed: %d", C, W, H, N, box_w,
+         box_h, (int)r);
+  return m;
+}
+
 CUtensorMap make_map_2d(const void* ptr, long long K, long long rows, int box_rows) {
   CUtensorMap m;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};

@@ -45,6 +45,9 @@ struct Error : std::runtime_error {
 // ------------------------------------------------------------------ tensor maps
 // A operand: bf16 NHWC tensor {C, W, H, N}, box {64, box_w, box_h, 1}, 128B swizzle, zero OOB fill.
 CUtensorMap make_map_4d(const void* ptr, int C, int W, int H, int N, int box_w, int box_h);
+// RAW segment source (gemm_tc.cuh): fp32 NHWC tensor {C, W, H, N}, box {64, box_w, box_h, 1}, NO swizzle (the
+// tile lands as 128 pixel rows of 256 bytes and is converted in shared memory)
+CUtensorMap make_map_4d_f32(const void* ptr, int C, int W, int H, int N, int box_w, int box_h);
 // B operand: bf16 K-major matrix {K, rows}, box {64, box_rows}, 128B swizzle.
 CUtensorMap make_map_2d(const void* ptr, long long K, long long rows, int box_rows);
 // f16f8 fp8 rows (common.cuh): byte tensors with 2 bytes per channel element, {2C, W, H, N} /

@@ -223,6 +223,42 @@ void launch_gn_stats(const float* src, double* acc, int B, int HW, int Cs, int C
   launch_pdl(gn_stats_kernel, grid, dim3(256), 0, s, src, acc, HW, Cs, Ctot, coff, ppb);
 }
 
+// GroupNorm finalize for a RAW GEMM segment (gemm_tc.cuh): per-(sample, channel) scale = gamma * rstd and
+// shift = beta - mean * scale from the producers' fp64 sums; one block per sample, one thread per channel.
+__global__ void __launch_bounds__(512) gn_finalize_kernel(const double* __restrict__ stats,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, int groups,
+                                                          int HW, int C, float* __restrict__ scale,
+                                                          float* __restrict__ shift) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.x;
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    double ts = 0.0, tq = 0.0;
+    for (int i = 0; i < cpg; ++i) {
+      const double* st = stats + (static_cast<long long>(b) * C + g * cpg + i) * 2;
+      ts += st[0];
+      tq += st[1];
+    }
+    const double n = static_cast<double>(HW) * cpg;
+    const double mean = ts / n;
+    double var = tq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * rstd;
+    scale[static_cast<long long>(b) * C + c] = sc;
+    shift[static_cast<long long>(b) * C + c] = beta[c] - static_cast<float>(mean) * sc;
+  }
+}
+
+void launch_gn_finalize(const double* stats, const float* gamma, const float* beta, float eps, int groups,
+                        int B, int HW, int C, float* scale, float* shift, cudaStream_t s) {
+  launch_pdl(gn_finalize_kernel, dim3(B), dim3(C < 512 ? C : 512), 0, s, stats, gamma, beta, eps, groups, HW,
+             C, scale, shift);
+}
+
 // ------------------------------------------------------------------------------------------------
 // act_split: fp32 NHWC (one or two concatenated sources) -> split bf16 operand tensor(s).
 // GroupNorm is finalised in the block prologue from the per-(sample, channel) fp64 sums the

@@ -23,6 +23,10 @@ void launch_conv_in(const float* x, const float* w, const float* bias, float* ou
 // feature map gets its statistics from the producing GEMM's epilogue)
 void launch_gn_stats(const float* src, double* acc, int B, int HW, int Cs, int Ctot, int coff,
                      cudaStream_t s);
+// scale[b][c] = gamma[c] * rstd(b, group(c)), shift[b][c] = beta[c] - mean * scale from the fp64 sums
+// [B][C][2] (the same arithmetic as the operand transform's prologue); operand of a RAW GEMM segment
+void launch_gn_finalize(const double* stats, const float* gamma, const float* beta, float eps, int groups,
+                        int B, int HW, int C, float* scale, float* shift, cudaStream_t s);
 enum XformLayout : int { XF_SAME = 0, XF_UP2 = 1, XF_S2D = 2 };
 // Operand transform: out_hi/lo[b, y', x', c] = split(act(GN(cat(src0, src1)))); act = SiLU if silu.
 // GroupNorm(groups, eps, gamma, beta) is applied when stats0 != null, using the per-(sample, channel)

@@ -394,6 +394,8 @@ struct Builder {
   std::vector<void*> deferred_free;
   double* gn_pool = nullptr;
   size_t gn_pool_doubles = 0, gn_used = 0;
+  float* row_pool = nullptr;
+  size_t row_pool_floats = 0, row_used = 0;
   const float* emb_all = nullptr;  // [B, emb_total]
   const float* cross_cv = nullptr;  // [B, n_st * tf_layers * d_attn] cross-attention output vectors (n_cond == 1)
   long long cross_cv_ld = 0;
@@ -481,6 +483,16 @@ struct Builder {
     return acc;
   }
 
+  // per-row (sum, sum of squares) accumulator of a [rows, C] token tensor (LayerNorm statistics produced by a
+  // GEMM epilogue for a RAW consumer); zeroed with the GroupNorm pool at the start of every forward
+  float* new_rowstats(long long rows) {
+    PF_CHECK(lane < 0, "row statistics inside a lane section");
+    float* r = row_pool + row_used;
+    row_used += static_cast<size_t>(rows) * 2;
+    PF_CHECK(dry || row_used <= row_pool_floats, "row statistics pool overflow");
+    return r;
+  }
+
   // statistics of a tensor: taken from the producing GEMM's epilogue when available, otherwise a
   // dedicated reduction pass
   const double* stats_of(const T& x) {
@@ -560,7 +572,71 @@ struct Builder {
     int W, H, N;  // TMA dims 1..3
     int kind;     // 0 = 1x1 (no shift), 1 = 3x3, 2 = 3x3 stride-2 over S2D planes
     bool f8 = false;  // f16f8 operand (buf.hi = fp16, buf.lo = fp8 rows)
+    // RAW segment (kind 0 only, gemm_tc.cuh): the operand is formed inside the GEMM from fp32 NHWC tensors
+    // raw0 (rawC0 channels) [+ raw1 (C - rawC0 channels)]; `buf` is unused.  Optional per-row LayerNorm
+    // statistics (rowstats [rows][2], eps), per-(image, channel) affine (scale / shift, row stride raw_ld;
+    // 0 = one vector for all images) and SiLU, applied in that order.
+    const float* raw0 = nullptr;
+    const float* raw1 = nullptr;
+    int rawC0 = 0;
+    const float* scale = nullptr;
+    const float* shift = nullptr;
+    long long raw_ld = 0;
+    bool silu = false;
+    const float* rowstats = nullptr;
+    float eps = 0.f;
   };
+
+  // tile / kernel-family decisions of conv_gemm, shared with raw_variant_ok
+  struct GemmPick {
+    int bn, box_w, box_h;
+    bool two, stack, halo;
+  };
+  GemmPick pick_gemm(bool f8, int kind0, bool seg1_1x1_or_none, int Ho, int Wo, int Cout, int bn_override,
+                     bool f32_out) const {
+    // f16f8 convolutions with Cout % 256 == 0 can use 256-wide tiles (one accumulator stage, gemm_tc.cu
+    // NACC).  Measured on B200 (profiles/r3e_*): 600 vs 638 TF/s at K = 4608, 406 vs 420 at 16 x 16 -- the
+    // exposed epilogue costs more than the halved A operand reads buy, so PF_F8_BN256=1 is opt-in
+    static const bool f8_bn256 = std::getenv("PF_F8_BN256") && std::atoi(std::getenv("PF_F8_BN256")) != 0;
+    static const bool one_cta = std::getenv("PF_GEMM_1CTA") != nullptr;
+    // stacked [B_hi ; B_lo] operand (2 MMAs per K step, fewer smem operand reads) for BN <= 128;
+    // PF_GEMM_STACK = 0 (off) / 64 / 128 (only that tile width) for A/B measurements
+    static const int stack_sel = std::getenv("PF_GEMM_STACK") ? std::atoi(std::getenv("PF_GEMM_STACK")) : -1;
+    // halo stages for the N = 64 3x3 convolutions at 128 x 128 (tile = one image row): A bytes
+    // through L2 drop 2.95x (these launches were L2 -> SM bandwidth bound).  PF_GEMM_HALO=0 disables.
+    static const bool halo_ok = !(std::getenv("PF_GEMM_HALO") && std::atoi(std::getenv("PF_GEMM_HALO")) == 0);
+    GemmPick k;
+    k.box_w = choose_box_w(Wo);
+    PF_CHECK(128 % k.box_w == 0 && Wo % k.box_w == 0, "unsupported width %d", Wo);
+    k.box_h = 128 / k.box_w;
+    PF_CHECK(Ho % k.box_h == 0, "unsupported height %d for width %d", Ho, Wo);
+    const int tiles_per_img = (Wo / k.box_w) * (Ho / k.box_h);
+    // cta_group::2 (CTA pairs, 256-row tile pairs) whenever the M tiles pair up
+    k.two = !one_cta && ((B * tiles_per_img) % 2 == 0);
+    k.bn = bn_override ? bn_override : (f8 && f8_bn256 && k.two && Cout % 256 == 0) ? 256 : choose_bn(Cout);
+    PF_CHECK(!f8 || k.bn <= 128 || k.two, "f16f8 GEMM: BN=%d needs CTA pairs", k.bn);
+    k.stack = !f8 && k.two && k.bn <= 128 && (stack_sel < 0 || stack_sel == k.bn);
+    k.halo = halo_ok && f32_out && k.two && (k.stack || f8) && k.bn == 64 && k.box_w == 128 && k.box_h == 1 &&
+             kind0 == 1 && seg1_1x1_or_none;
+    return k;
+  }
+  // would a GEMM of this shape with a RAW segment and output variant v (gemm_tc.cu: 0 fp32, 1 fp32 + GroupNorm
+  // statistics, 2 split, 3 split transposed, 4 GeGLU, 5 f16f8 split, 6 fp32 + row statistics) find a kernel?
+  bool raw_variant_ok(bool f8, int kind0, bool has_seg1, int Ho, int Wo, int Cout, int bn_override, bool f32_out,
+                      int v) const {
+    static const bool raw_on = !(std::getenv("PF_RAW") && std::atoi(std::getenv("PF_RAW")) == 0);
+    if (!raw_on) return false;
+    const GemmPick k = pick_gemm(f8, kind0, true, Ho, Wo, Cout, bn_override, f32_out);
+    (void)has_seg1;
+    if (!k.two) return false;
+    GemmParams g;
+    memset(&g, 0, sizeof g);
+    g.f8 = f8; g.two_cta = 1; g.halo = k.halo; g.stack = k.stack; g.raw = 1;
+    g.mode = v == 2 ? OUT_SPLIT : v == 3 ? OUT_SPLIT_T : v == 4 ? OUT_GEGLU : v == 5 ? OUT_SPLIT8 : OUT_F32;
+    if (v == 1) g.stats = reinterpret_cast<double*>(8);
+    if (v == 6) g.rowstats = reinterpret_cast<float*>(8);
+    return gemm_kernel_available(g, k.bn);
+  }
 
   void fill_seg(GemmSeg& sg, const ASrc& a, PackedW& w, int b_box_rows, int box_w, int box_h,
                 bool halo = false) {
@@ -589,6 +665,28 @@ struct Builder {
     sg.a_rows = grouped ? GEMM_HALO_ROWS : 128;
     if (grouped) box_w = GEMM_HALO_ROWS;
     PF_CHECK(a.f8 == w.f8, "GEMM operand formats differ (activation f8=%d, weight f8=%d)", (int)a.f8, (int)w.f8);
+    if (a.raw0) {
+      PF_CHECK(a.kind == 0 && !grouped, "RAW segments are 1x1 only");
+      const int c0 = a.raw1 ? a.rawC0 : a.C;
+      PF_CHECK(c0 % 64 == 0 && (a.C - c0) % 64 == 0, "RAW segment: source channels %d+%d not multiples of 64", c0, a.C - c0);
+      sg.raw = 1;
+      sg.raw_c0 = c0;
+      sg.raw_silu = a.silu ? 1 : 0;
+      sg.raw_rowlen = a.C;
+      sg.raw_scale = a.scale;
+      sg.raw_shift = a.shift;
+      sg.raw_rowstats = a.rowstats;
+      sg.raw_ld = a.raw_ld;
+      sg.raw_eps = a.eps;
+      if (!dry) {
+        sg.a_hi = make_map_4d_f32(a.raw0, c0, a.W, a.H, a.N, box_w, box_h);
+        sg.a_lo = a.raw1 ? make_map_4d_f32(a.raw1, a.C - c0, a.W, a.H, a.N, box_w, box_h) : sg.a_hi;
+        auto& mp = wmaps(w, b_box_rows, dry);
+        sg.b_hi = mp.first;
+        sg.b_lo = mp.second;
+      }
+      return;
+    }
     if (!dry) {
       sg.a_hi = make_map_4d(a.buf.hi, a.C, a.W, a.H, a.N, box_w, box_h);
       sg.a_lo = a.f8 ? make_map_4d_u8(a.buf.lo, a.C, a.W, a.H, a.N, box_w, box_h)
@@ -604,40 +702,23 @@ struct Builder {
   // f32_out = false: the caller will select a split output mode (no halo kernel for those)
   Op& conv_gemm(const ASrc& a0, PackedW& w0, const ASrc* a1, PackedW* w1, int Ho, int Wo, int Cout,
                 int row0 = 0, int bn_override = 0, bool f32_out = true) {
-    // f16f8 convolutions with Cout % 256 == 0 can use 256-wide tiles (one accumulator stage, gemm_tc.cu
-    // NACC).  Measured on B200 (profiles/r3e_*): 600 vs 638 TF/s at K = 4608, 406 vs 420 at 16 x 16 -- the
-    // exposed epilogue costs more than the halved A operand reads buy, so PF_F8_BN256=1 is opt-in
-    static const bool f8_bn256 = std::getenv("PF_F8_BN256") && std::atoi(std::getenv("PF_F8_BN256")) != 0;
-    const bool pairs = (B * ((Wo / choose_box_w(Wo)) * (Ho / (128 / choose_box_w(Wo))))) % 2 == 0;
-    const int bn = bn_override ? bn_override
-                               : (a0.f8 && f8_bn256 && pairs && Cout % 256 == 0 && std::getenv("PF_GEMM_1CTA") == nullptr)
-                                     ? 256 : choose_bn(Cout);
-    const int box_w = choose_box_w(Wo);
-    PF_CHECK(128 % box_w == 0 && Wo % box_w == 0, "unsupported width %d", Wo);
-    const int box_h = 128 / box_w;
-    PF_CHECK(Ho % box_h == 0, "unsupported height %d for width %d", Ho, Wo);
+    const GemmPick pk = pick_gemm(a0.f8, a0.kind, !a1 || a1->kind == 0, Ho, Wo, Cout, bn_override, f32_out);
+    const int bn = pk.bn, box_w = pk.box_w, box_h = pk.box_h;
+    const bool two = pk.two, halo = pk.halo;
     Op& op = push(OP_GEMM);
     op.bn = bn;
     GemmParams& g = op.g;
     g.tiles_x = Wo / box_w;
     g.tiles_per_img = g.tiles_x * (Ho / box_h);
-    // cta_group::2 (CTA pairs, 256-row tile pairs) whenever the M tiles pair up
-    static const bool one_cta = std::getenv("PF_GEMM_1CTA") != nullptr;
-    const bool two = !one_cta && ((B * g.tiles_per_img) % 2 == 0);
     g.two_cta = two ? 1 : 0;
-    // stacked [B_hi ; B_lo] operand (2 MMAs per K step, fewer smem operand reads) for BN <= 128;
-    // PF_GEMM_STACK = 0 (off) / 64 / 128 (only that tile width) for A/B measurements
-    static const int stack_sel = std::getenv("PF_GEMM_STACK") ? std::atoi(std::getenv("PF_GEMM_STACK")) : -1;
     g.f8 = a0.f8 ? 1 : 0;
     PF_CHECK(!a1 || a1->f8 == a0.f8, "GEMM segments with different operand formats");
-    PF_CHECK(!g.f8 || bn <= 128 || two, "f16f8 GEMM: BN=%d needs CTA pairs", bn);
-    g.stack = (!g.f8 && two && bn <= 128 && (stack_sel < 0 || stack_sel == bn)) ? 1 : 0;
-    // halo stages for the N = 64 3x3 convolutions at 128 x 128 (tile = one image row): A bytes
-    // through L2 drop 2.95x (these launches were L2 -> SM bandwidth bound).  PF_GEMM_HALO=0 disables.
-    static const bool halo_ok = !(std::getenv("PF_GEMM_HALO") && std::atoi(std::getenv("PF_GEMM_HALO")) == 0);
-    const bool halo = halo_ok && f32_out && two && (g.stack || g.f8) && bn == 64 && box_w == 128 && box_h == 1 && a0.kind == 1 &&
-                      (!a1 || a1->kind == 0);
+    g.stack = pk.stack ? 1 : 0;
     g.halo = halo ? 1 : 0;
+    g.raw = (a0.raw0 || (a1 && a1->raw0)) ? 1 : 0;
+    static const int raw_dbg = std::getenv("PF_RAW_DBG") ? std::atoi(std::getenv("PF_RAW_DBG")) : 0;
+    g.raw_dbg = raw_dbg;
+    PF_CHECK(!g.raw || two, "RAW GEMM segments need CTA pairs");
     fill_seg(g.seg[0], a0, w0, two ? bn / 2 : bn, box_w, box_h, halo);
     g.seg[0].b_row0 = row0;
     g.nseg = 1;
@@ -691,9 +772,16 @@ struct Builder {
     const size_t npix = static_cast<size_t>(B) * H * Wd;
     const bool f8 = conv_f8(static_cast<long long>(H) * Wd, static_cast<long long>(H) * Wd);
     const bool f8_up = conv_f8(static_cast<long long>(H) * Wd, 4ll * H * Wd);  // format an UpSample consumer wants
+    // 1x1 skip conv (cin != cout): its operand is the PLAIN input.  With a RAW segment the second GEMM reads
+    // the fp32 input tensors directly and converts them in shared memory (gemm_tc.cu); otherwise the
+    // transform below writes a second, un-normalised operand in the same pass.
+    static const bool raw_skip_on = !(std::getenv("PF_RAW_SKIP") && std::atoi(std::getenv("PF_RAW_SKIP")) == 0);
+    const bool raw_skip = L.cin != L.cout && raw_skip_on && x0.p && (!x1 || x1->p) && x0.C % 64 == 0 &&
+                          (!x1 || x1->C % 64 == 0) &&
+                          raw_variant_ok(f8, 1, true, H, Wd, L.cout, 0, !split_only, split_only ? (f8_up ? 5 : 2) : 1);
     Split a3;  // plain split of the input for the 1x1 skip conv (same pass as the normalised one)
     Split a1 = act_split(x0, x1, L.name + ".in_layers.0", 1e-5f, true, XF_SAME,
-                         L.cin != L.cout ? &a3 : nullptr, f8);
+                         (L.cin != L.cout && !raw_skip) ? &a3 : nullptr, f8);
     T h1;
     h1.C = L.cout; h1.H = H; h1.W = Wd;
     h1.p = alloc<float>(npix * L.cout);
@@ -721,6 +809,11 @@ struct Builder {
     if (L.cin != L.cout) {
       PackedW& ws = W(m, L.name + ".skip_connection.weight", {L.name + ".skip_connection.weight"}, 0, f8);
       ASrc s3{a3, C, Wd, H, B, 0, f8};
+      if (raw_skip) {
+        s3.raw0 = x0.p;
+        s3.raw1 = x1 ? x1->p : nullptr;
+        s3.rawC0 = x0.C;
+      }
       const float* bsum = Fsum(m, L.name + ".out_layers.3.bias", L.name + ".skip_connection.bias");
       Op& op = conv_gemm(s2, w2, &s3, &ws, H, Wd, L.cout, 0, 0, !split_only);
       if (split_only) out_split(op, y.sp, L.cout, bsum, 0, nullptr, 0, f8_up);
@@ -859,25 +952,81 @@ struct Builder {
     PF_CHECK(N % 128 == 0, "SpatialTransformer: %d tokens per image is not a multiple of 128", N);
     const long long rows = static_cast<long long>(B) * N;
     const int sti = st_index++;
-    Split a = act_split(x, nullptr, L.name + ".norm", 1e-6f, false, XF_SAME);
+    const int Fh = 4 * C;
+    const int bn_geglu = (2 * Fh) % 256 == 0 ? 256 : choose_bn(2 * Fh);
+    // RAW operands (gemm_tc.cu): GroupNorm -> proj_in and LayerNorm -> q/k/v, to_q (cross), GeGLU projection are
+    // applied by the consumer GEMM's conversion warps to the fp32 tensor; the LayerNorm row statistics come from
+    // the producing GEMM's epilogue.  PF_RAW_GN=0 / PF_RAW_LN=0 restore the separate transform passes.
+    static const bool raw_gn_on = !(std::getenv("PF_RAW_GN") && std::atoi(std::getenv("PF_RAW_GN")) == 0);
+    static const bool raw_ln_on = !(std::getenv("PF_RAW_LN") && std::atoi(std::getenv("PF_RAW_LN")) == 0);
+    const bool ln_qkv = raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, 2 * C, 0, false, 2) &&
+                        raw_variant_ok(false, 0, false, H, Wd, C, 0, false, 3);
+    const bool ln_ff = raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, 2 * Fh, bn_geglu, false, 4);
+    const bool ln_q2 = raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, C, 0, false, 2);
+    const bool raw_gn = raw_gn_on && x.p && raw_variant_ok(false, 0, false, H, Wd, C, 0, true, ln_qkv ? 6 : 0);
     float* t0 = alloc<float>(rows * C);
+    float* rs_t0 = ln_qkv ? new_rowstats(rows) : nullptr;  // row statistics of the current residual stream
     {
       PackedW& w = W(m, L.name + ".proj_in.weight", {L.name + ".proj_in.weight"});
-      ASrc s{a, C, Wd, H, B, 0};
-      Op& op = conv_gemm(s, w, nullptr, nullptr, H, Wd, C);
-      out_f32(op, t0, C, F(m, L.name + ".proj_in.bias"), 0, nullptr, 0);
+      const float* gamma = F(m, L.name + ".norm.weight");
+      const float* beta = F(m, L.name + ".norm.bias");
+      if (raw_gn) {
+        PF_CHECK(C % 32 == 0, "GroupNorm channels %d not divisible by 32", C);
+        const double* st = stats_of(x);
+        float* sc = alloc<float>(static_cast<size_t>(B) * C);
+        float* sh = alloc<float>(static_cast<size_t>(B) * C);
+        Op& fo = push(OP_GN_FINALIZE);
+        fo.p[0] = st; fo.p[1] = gamma; fo.p[2] = beta;
+        fo.o[0] = sc; fo.o[1] = sh;
+        fo.i[0] = B; fo.i[1] = N; fo.i[2] = C; fo.i[3] = 32;
+        fo.f = 1e-6f;
+        ASrc s{Split(), C, Wd, H, B, 0};
+        s.raw0 = x.p;
+        s.scale = sc; s.shift = sh; s.raw_ld = C;
+        Op& op = conv_gemm(s, w, nullptr, nullptr, H, Wd, C);
+        out_f32(op, t0, C, F(m, L.name + ".proj_in.bias"), 0, nullptr, 0);
+        op.g.rowstats = rs_t0;
+        afree(sc);
+        afree(sh);
+      } else {
+        Split a = act_split(x, nullptr, L.name + ".norm", 1e-6f, false, XF_SAME);
+        ASrc s{a, C, Wd, H, B, 0};
+        Op& op = conv_gemm(s, w, nullptr, nullptr, H, Wd, C);
+        out_f32(op, t0, C, F(m, L.name + ".proj_in.bias"), 0, nullptr, 0);
+        op.g.rowstats = rs_t0;
+        free_split(a);
+      }
     }
-    free_split(a);
+    // LayerNorm'd operand of a [rows, C] fp32 tensor: RAW (row statistics from the producer) or a transform pass
+    auto ln_operand = [&](const float* src, const float* rs, const std::string& prefix, Split& tmp) {
+      ASrc s{Split(), C, Wd, H, B, 0};
+      if (rs) {
+        s.raw0 = src;
+        s.rowstats = rs;
+        s.eps = 1e-5f;
+        s.scale = F(m, prefix + ".weight");
+        s.shift = F(m, prefix + ".bias");
+        s.raw_ld = 0;
+      } else {
+        tmp = ln_split(src, rows, C, prefix);
+        s.buf = tmp;
+      }
+      return s;
+    };
 
     PF_CHECK(c.tf_layers >= 1, "SpatialTransformer without transformer blocks");
     Split ao;  // operand of proj_out
     for (int li = 0; li < c.tf_layers; ++li) {
       const std::string tb = L.name + ".transformer_blocks." + std::to_string(li);
       // ---- self attention: x = attn1(norm1(x)) + x
-      Split l1 = ln_split(t0, rows, C, tb + ".norm1");
+      if (m->packing) {  // both LayerNorm forms need the affine vectors
+        F(m, tb + ".norm1.weight"); F(m, tb + ".norm1.bias");
+        F(m, tb + ".norm3.weight"); F(m, tb + ".norm3.bias");
+      }
+      Split l1;
+      ASrc sl = ln_operand(t0, rs_t0, tb + ".norm1", l1);
       Split qk = alloc_split(rows * 2 * C);
       Split vt = alloc_split(rows * C);
-      ASrc sl{l1, C, Wd, H, B, 0};
       {
         PackedW& w = W(m, tb + ".attn1.qkv", {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight",
                                              tb + ".attn1.to_v.weight"});
@@ -915,24 +1064,29 @@ struct Builder {
         W(m, tb + ".attn2.to_out.0.weight", {tb + ".attn2.to_out.0.weight"});
       }
       float* xattn = nullptr;
+      float* rs_attn = nullptr;  // row statistics of xattn (input of norm3)
       if (n_cond == 1) {
         // cross-attention with one key: the per-sample vector computed up front (build())
         Op& op = conv_gemm(so, wo, nullptr, nullptr, H, Wd, C);
         out_f32(op, x1, C, cross_cv + static_cast<size_t>(sti * c.tf_layers + li) * C, cross_cv_ld, t0, C);
+        rs_attn = ln_ff ? new_rowstats(rows) : nullptr;
+        op.g.rowstats = rs_attn;
         free_split(o);
         xattn = x1;
       } else {
+        float* rs_x1 = ln_q2 ? new_rowstats(rows) : nullptr;
         Op& op = conv_gemm(so, wo, nullptr, nullptr, H, Wd, C);
         out_f32(op, x1, C, F(m, tb + ".attn1.to_out.0.bias"), 0, t0, C);
+        op.g.rowstats = rs_x1;
         free_split(o);
         // ---- cross attention: x = attn2(norm2(x), cond) + x
         PF_CHECK(n_cond % 128 == 0 && n_cond <= 1024 && c.d_cond % 64 == 0,
                  "cross-attention supports n_cond == 1 or n_cond %% 128 == 0 (<= 1024) with d_cond %% 64 == 0; "
                  "got n_cond=%d d_cond=%d", n_cond, c.d_cond);
-        Split l2 = ln_split(x1, rows, C, tb + ".norm2");
+        Split l2;
         Split q2 = alloc_split(rows * C);
         {
-          ASrc s{l2, C, Wd, H, B, 0};
+          ASrc s = ln_operand(x1, rs_x1, tb + ".norm2", l2);
           Op& opq = conv_gemm(s, W(m, tb + ".attn2.to_q.weight", {}), nullptr, nullptr, H, Wd, C);
           opq.g.mode = OUT_SPLIT;
           opq.g.out_hi = q2.hi; opq.g.out_lo = q2.lo; opq.g.ldc = C;
@@ -968,20 +1122,21 @@ struct Builder {
         ASrc s2{o2, C, Wd, H, B, 0};
         Op& op2 = conv_gemm(s2, W(m, tb + ".attn2.to_out.0.weight", {}), nullptr, nullptr, H, Wd, C);
         out_f32(op2, x2, C, F(m, tb + ".attn2.to_out.0.bias"), 0, x1, C);
+        rs_attn = ln_ff ? new_rowstats(rows) : nullptr;
+        op2.g.rowstats = rs_attn;
         free_split(o2);
         afree(x1);
         xattn = x2;
       }
       afree(t0);
       // ---- feed forward: x = ff(norm3(x)) + x   (GeGLU, unet_attention.py:296-333)
-      Split l3 = ln_split(xattn, rows, C, tb + ".norm3");
-      const int Fh = 4 * C;
+      Split l3;
       Split e = alloc_split(rows * Fh);
       {
         // GeGLU fused into the projection's epilogue: weight rows are interleaved so every BN-wide
         // tile holds [BN/2 value | BN/2 gate] columns of the same output features
-        const int bn = (2 * Fh) % 256 == 0 ? 256 : choose_bn(2 * Fh);
-        ASrc s{l3, C, Wd, H, B, 0};
+        const int bn = bn_geglu;
+        ASrc s = ln_operand(xattn, rs_attn, tb + ".norm3", l3);
         Op& op = conv_gemm(s, W(m, tb + ".ff.net.0.proj.weight:geglu" + std::to_string(bn / 2),
                                 {tb + ".ff.net.0.proj.weight"}, bn / 2),
                            nullptr, nullptr, H, Wd, 2 * Fh, 0, bn);
@@ -1005,6 +1160,8 @@ struct Builder {
         } else {
           x3 = alloc<float>(rows * C);
           out_f32(op, x3, C, F(m, tb + ".ff.net.2.bias"), 0, xattn, C);
+          rs_t0 = ln_qkv ? new_rowstats(rows) : nullptr;
+          op.g.rowstats = rs_t0;
         }
       }
       free_split(e);
@@ -1131,10 +1288,28 @@ struct Builder {
       count_block(m->middle);
       for (auto& b : m->output_blocks) count_block(b);
       gn_pool_doubles = doubles;
-      gn_pool = alloc<double>(doubles);
+      // LayerNorm row statistics: up to 3 per transformer block, [tokens][2] fp32 each
+      size_t rfloats = 0;
+      {
+        int h = H, w = Wd;
+        auto walk = [&](const BlockSpec& b) {
+          for (auto& l : b.layers) {
+            if (l.kind == Layer::ST) rfloats += static_cast<size_t>(3) * c.tf_layers * B * h * w * 2;
+            if (l.kind == Layer::DOWN) { h /= 2; w /= 2; }
+            if (l.kind == Layer::UP) { h *= 2; w *= 2; }
+          }
+        };
+        for (auto& b : m->input_blocks) walk(b);
+        walk(m->middle);
+        for (auto& b : m->output_blocks) walk(b);
+      }
+      row_pool_floats = rfloats;
+      char* pool = alloc<char>(doubles * sizeof(double) + rfloats * sizeof(float));
+      gn_pool = reinterpret_cast<double*>(pool);
+      row_pool = reinterpret_cast<float*>(pool + doubles * sizeof(double));
       Op& op = push(OP_MEMSET);
-      op.o[0] = gn_pool;
-      op.i[0] = static_cast<long long>(doubles * sizeof(double));
+      op.o[0] = pool;
+      op.i[0] = static_cast<long long>(doubles * sizeof(double) + rfloats * sizeof(float));
     }
     // ---- time embedding (unet.py:64-68, 151-169, 182) and all ResBlock emb projections
     if (m->time_lut && !m->packing) {
@@ -1356,6 +1531,10 @@ struct Builder {
       }
     }
     if (!out_done) out_conv(x);
+    for (const Op& op : plan->ops)
+      if (op.kind == OP_GEMM)
+        PF_CHECK(gemm_kernel_available(op.g, op.bn), "no GEMM kernel for bn=%d mode=%d f8=%d two=%d halo=%d raw=%d",
+                 op.bn, op.g.mode, op.g.f8, op.g.two_cta, op.g.halo, op.g.raw);
   }
 
   // ---------------------------------------------------------------- lanes
@@ -1490,8 +1669,11 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
         launch_gn_stats(static_cast<const float*>(op.p[0]), static_cast<double*>(op.o[0]), (int)op.i[0],
                         (int)op.i[1], (int)op.i[2], (int)op.i[3], (int)op.i[4], s);
         break;
-      case OP_GN_FINALIZE:
-        break;  // (retired: GroupNorm is finalised inside the operand transform / final conv)
+      case OP_GN_FINALIZE:  // per-(sample, channel) scale / shift for a RAW GEMM segment
+        launch_gn_finalize(static_cast<const double*>(op.p[0]), static_cast<const float*>(op.p[1]),
+                           static_cast<const float*>(op.p[2]), op.f, (int)op.i[3], (int)op.i[0], (int)op.i[1],
+                           (int)op.i[2], static_cast<float*>(op.o[0]), static_cast<float*>(op.o[1]), s);
+        break;
       case OP_ACT_SPLIT: {
         ActSplitArgs a = op.as;
         if (op.ext == EXT_COND) a.src0 = cond + op.ext_off;
@@ -1853,10 +2035,11 @@ int pf_unet_op_desc(pf_unet* h, int32_t i, char* buf, int32_t len) {
       const GemmParams& g = op.g;
       int k = 0;
       for (int s = 0; s < g.nseg; ++s) k += g.seg[s].ntaps * g.seg[s].kb_per_tap * 64;
-      snprintf(buf, len, "gemm M=%lld N=%d K=%d bn=%d taps=%d nseg=%d z=%d mode=%d stages=%d cta%d%s",
+      snprintf(buf, len, "gemm M=%lld N=%d K=%d bn=%d taps=%d nseg=%d z=%d mode=%d stages=%d cta%d%s%s%s",
                static_cast<long long>(g.m_tiles) * 128, g.n_tiles * op.bn, k, op.bn, g.seg[0].ntaps,
                g.nseg, g.z_count, g.mode, g.nstages, g.two_cta ? 2 : 1,
-               g.halo ? "sh" : (g.two_cta && g.stack && op.bn <= 128) ? "s" : "");
+               g.halo ? "sh" : (g.two_cta && g.stack && op.bn <= 128) ? "s" : "", g.raw ? " raw" : "",
+               g.rowstats ? " rowstats" : "");
     } else if (op.kind == OP_ACT_SPLIT) {
       snprintf(buf, len, "act_split C=%d+%d HxW=%dx%d B=%d norm=%d silu=%d layout=%d dual=%d", op.as.C0,
                op.as.C1, op.as.H, op.as.W, op.as.B, op.as.stats0 != nullptr, op.as.silu, op.as.layout,
