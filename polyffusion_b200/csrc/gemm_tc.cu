@@ -553,7 +553,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           }
         }
       } else {
-        constexpr bool geglu = (MODE == OUT_GEGLU);
+        constexpr bool geglu = (MODE == OUT_GEGLU || MODE == OUT_GEGLU8);
         const int ncols = geglu ? BN / 2 : BN;          // output columns produced by this tile
         const int ocol0 = geglu ? (tc.n0 / 2) : tc.n0;  // first output column
         const float* av = p.addvec ? p.addvec + static_cast<long long>(tc.img) * p.addvec_ld : nullptr;
@@ -642,9 +642,9 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 rsum[it] += (o.x + o.y) + (o.z + o.w);
                 rsq[it] = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, rsq[it]))));
               }
-            } else if constexpr (MODE == OUT_SPLIT8) {
+            } else if constexpr (MODE == OUT_SPLIT8 || MODE == OUT_GEGLU8) {
               // f16f8 activation operand: h16 [m, ldc] fp16 + fp8 rows [m][ldc / 64][h8 x 64 | l8 x 64]
-              if (has_res) {
+              if (MODE == OUT_SPLIT8 && has_res) {
                 o.x += rres[it].x; o.y += rres[it].y; o.z += rres[it].z; o.w += rres[it].w;
               }
               uint2 h16;
@@ -839,7 +839,8 @@ static GemmKernel pick_variant(int v) {
       case 3: return gemm_tc2s_kernel<BN, OUT_SPLIT_T, false>;
       case 5: return gemm_tc2s_kernel<BN, OUT_SPLIT8, false>;
       case 6: return gemm_tc2s_kernel<BN, OUT_F32, 2>;
-      default: return gemm_tc2s_kernel<BN, OUT_GEGLU, false>;
+      case 4: return gemm_tc2s_kernel<BN, OUT_GEGLU, false>;
+      default: return nullptr;
     }
   } else if constexpr (KIND == 1) {
     switch (v) {
@@ -849,7 +850,8 @@ static GemmKernel pick_variant(int v) {
       case 3: return gemm_tc2_kernel<BN, OUT_SPLIT_T, false>;
       case 5: return gemm_tc2_kernel<BN, OUT_SPLIT8, false>;
       case 6: return gemm_tc2_kernel<BN, OUT_F32, 2>;
-      default: return gemm_tc2_kernel<BN, OUT_GEGLU, false>;
+      case 4: return gemm_tc2_kernel<BN, OUT_GEGLU, false>;
+      default: return nullptr;
     }
   } else {
     switch (v) {
@@ -859,7 +861,8 @@ static GemmKernel pick_variant(int v) {
       case 3: return gemm_tc_kernel<BN, OUT_SPLIT_T, false>;
       case 5: return gemm_tc_kernel<BN, OUT_SPLIT8, false>;
       case 6: return gemm_tc_kernel<BN, OUT_F32, 2>;
-      default: return gemm_tc_kernel<BN, OUT_GEGLU, false>;
+      case 4: return gemm_tc_kernel<BN, OUT_GEGLU, false>;
+      default: return nullptr;
     }
   }
 }
@@ -878,6 +881,7 @@ static GemmKernel pick_f8(int kind, int v) {
       case 1: return gemm_tc2f_kernel<BN, OUT_F32, true>;
       case 2: return gemm_tc2f_kernel<BN, OUT_SPLIT, false>;
       case 5: return gemm_tc2f_kernel<BN, OUT_SPLIT8, false>;
+      case 7: return gemm_tc2f_kernel<BN, OUT_GEGLU8, false>;
       default: return nullptr;
     }
   }
@@ -946,7 +950,7 @@ static GemmKernel pick_kernel(int bn, int kind, int v, bool raw = false) {
 cudaError_t gemm_init_attrs() {
   for (int bn : {64, 128, 256})
     for (int kind = 0; kind < 7; ++kind)
-      for (int v = 0; v < 7; ++v)
+      for (int v = 0; v < 8; ++v)
         for (int raw = 0; raw < 2; ++raw) {
           GemmKernel k = pick_kernel(bn, kind, v, raw != 0);
           if (!k) continue;
@@ -967,6 +971,7 @@ static int gemm_variant(const GemmParams& p) {
     case OUT_SPLIT: return 2;
     case OUT_SPLIT_T: return 3;
     case OUT_SPLIT8: return 5;
+    case OUT_GEGLU8: return 7;
     default: return 4;
   }
 }
@@ -975,20 +980,22 @@ bool gemm_kernel_available(const GemmParams& p, int bn) {
 }
 
 cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t stream) {
-  int v;
-  switch (p.mode) {
-    case OUT_F32: v = p.stats ? 1 : p.rowstats ? 6 : 0; break;
-    case OUT_SPLIT: v = 2; break;
-    case OUT_SPLIT_T: v = 3; break;
-    case OUT_SPLIT8: v = 5; break;
-    default: v = 4; break;
-  }
-  const int kind = p.f8 ? (p.two_cta ? (p.halo ? 5 : 4) : 6)
-                        : p.two_cta ? (p.halo ? 3 : (p.stack && bn <= 128) ? 2 : 1) : 0;
+  const int v = gemm_variant(p);
+  const int kind = gemm_kind(p, bn);
   GemmKernel k = pick_kernel(bn, kind, v, p.raw != 0);
   if (!k) return cudaErrorInvalidValue;
   if (p.raw && !p.two_cta) return cudaErrorInvalidValue;
-  const int nthreads = p.raw ? GEMM_RAW_THREADS : GEMM_THREADS;
+  bool raw_kernel = p.raw != 0;
+  // (timing experiment) PF_RAW_FORCE=1: run launches without raw segments on the 512-thread RAW kernels too
+  static const bool raw_force = std::getenv("PF_RAW_FORCE") != nullptr;
+  if (raw_force && !raw_kernel && p.two_cta) {
+    GemmKernel kr = pick_kernel(bn, kind, v, true);
+    if (kr) {
+      k = kr;
+      raw_kernel = true;
+    }
+  }
+  const int nthreads = raw_kernel ? GEMM_RAW_THREADS : GEMM_THREADS;
   if (p.two_cta) {
     const int smem = p.nstages * (p.halo ? gemm_stage_bytes2_halo(bn) : gemm_stage_bytes2(bn)) + 1024 +
                      gemm_epilogue_smem_bytes(bn);

@@ -32,6 +32,7 @@ enum GemmOutMode : int {
   OUT_GEGLU = 3,      // tile = [BN/2 value cols | BN/2 gate cols]: split-bf16 of (x+b)*gelu(g+b)
   OUT_SPLIT8 = 4,     // f16f8 activation operand of (acc + addvec + resid): out_hi = fp16 [m, ldc],
                       // out_lo = fp8 rows [m][ldc / 64][h8 x 64 | l8 x 64] (common.cuh)
+  OUT_GEGLU8 = 5,     // OUT_GEGLU with the result stored as an f16f8 activation operand
 };
 
 struct alignas(64) GemmSeg {

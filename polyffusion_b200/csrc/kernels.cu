@@ -300,29 +300,55 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_scale[512], s_shift[512];
+  __shared__ double2 s_st[512];
+  __shared__ float s_gmean[32], s_grstd[32];
   const int C = a.C0 + a.C1;
   const int b = blockIdx.y;
   const bool norm = a.stats0 != nullptr;
   if (norm) {
+    // GroupNorm finalize.  Every thread fetches the (sum, sum of squares) pair and the affine pair of its own
+    // channel(s) -- ONE round trip to L2 for the whole block (the per-thread loop over the channels of a group
+    // this replaces issued its loads one after the other: 19.9 -> 17.6 us per launch on the 16 x 16 maps, where a
+    // block only streams 128 KB).  One thread per group then reduces from shared memory (same summation order as
+    // before) and takes the fp64 square root; one thread per channel forms scale / shift.
     const int cpg = C / a.groups;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const int g = c / cpg;
+    float gam[4] = {0.f, 0.f, 0.f, 0.f}, bet[4] = {0.f, 0.f, 0.f, 0.f};  // C <= 512, blockDim >= 128
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = threadIdx.x + k * blockDim.x;
+      if (c < C) {
+        gam[k] = __ldg(a.gamma + c);
+        bet[k] = __ldg(a.beta + c);
+        s_st[c] = c < a.C0 ? __ldcg(reinterpret_cast<const double2*>(a.stats0 + (static_cast<long long>(b) * a.C0 + c) * 2))
+                           : __ldcg(reinterpret_cast<const double2*>(a.stats1 + (static_cast<long long>(b) * a.C1 + (c - a.C0)) * 2));
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < a.groups) {
+      const int g = threadIdx.x;
       double ts = 0.0, tq = 0.0;
       for (int i = 0; i < cpg; ++i) {
-        const int ch = g * cpg + i;
-        const double* st = ch < a.C0 ? a.stats0 + (static_cast<long long>(b) * a.C0 + ch) * 2
-                                     : a.stats1 + (static_cast<long long>(b) * a.C1 + (ch - a.C0)) * 2;
-        ts += st[0];
-        tq += st[1];
+        const double2 st = s_st[g * cpg + i];
+        ts += st.x;
+        tq += st.y;
       }
       const double n = static_cast<double>(a.H) * a.W * cpg;
       const double mean = ts / n;
       double var = tq / n - mean * mean;
       if (var < 0.0) var = 0.0;
-      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
-      const float sc = a.gamma[c] * rstd;
-      s_scale[c] = sc;
-      s_shift[c] = a.beta[c] - static_cast<float>(mean) * sc;
+      s_gmean[g] = static_cast<float>(mean);
+      s_grstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = threadIdx.x + k * blockDim.x;
+      if (c < C) {
+        const int g = c / cpg;
+        const float sc = gam[k] * s_grstd[g];
+        s_scale[c] = sc;
+        s_shift[c] = bet[k] - s_gmean[g] * sc;
+      }
     }
     __syncthreads();
   }
@@ -390,6 +416,9 @@ void launch_act_split(const ActSplitArgs& a, cudaStream_t s) {
   // PF_ACT_THREADS=128: blocks small enough (64 registers per thread) to sit beside a register-capped
   // GEMM CTA in the half-batch lane experiment (unet.cu); 256 is the measured best otherwise
   static const int threads = std::getenv("PF_ACT_THREADS") ? std::atoi(std::getenv("PF_ACT_THREADS")) : 256;
+  // Measured alternatives on B200, batch 64 (profiles/r4i_*, r4j_*; sum over the 47 transforms of one step):
+  // 1 / 2 / 8 items per thread 4.76 / 4.27 / 4.17 ms against 3.98 ms with 4; issuing the loads of item k + 1
+  // before item k is processed (77 registers, 3 blocks per SM, or capped at 64 registers for 4) 4.31 / 4.11 ms.
   dim3 grid(static_cast<unsigned>((items + threads * AS_IPT - 1) / (threads * AS_IPT)), a.B);
   launch_pdl(act_split_kernel, grid, dim3(threads), 0, s, a);
 }
@@ -413,7 +442,7 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
                                                        const float* __restrict__ beta, float eps,
                                                        bf16* __restrict__ out_hi,
                                                        bf16* __restrict__ out_lo, long long rows,
-                                                       int C) {
+                                                       int C, int fmt8) {
   pdl_wait();
   pdl_trigger();
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -448,18 +477,28 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
       const float o1 = (v[i].y - mean) * rstd * g.y + bb.y;
       const float o2 = (v[i].z - mean) * rstd * g.z + bb.z;
       const float o3 = (v[i].w - mean) * rstd * g.w + bb.w;
-      uint2 h, l;
-      split2(o0, o1, h.x, l.x);
-      split2(o2, o3, h.y, l.y);
-      *reinterpret_cast<uint2*>(out_hi + row * C + c0) = h;
-      *reinterpret_cast<uint2*>(out_lo + row * C + c0) = l;
+      if (fmt8) {  // f16f8 operand (common.cuh): fp16 [row][C] + fp8 rows [row][C / 64][h8 x 64 | l8 x 64]
+        uint2 h16;
+        uint32_t h8, l8;
+        split_f8x4(o0, o1, o2, o3, 1.f, F8_ACT_LO_SCALE, h16, h8, l8);
+        *reinterpret_cast<uint2*>(out_hi + row * C + c0) = h16;
+        uint8_t* p8 = reinterpret_cast<uint8_t*>(out_lo) + row * C * 2 + (c0 >> 6) * 128 + (c0 & 63);
+        *reinterpret_cast<uint32_t*>(p8) = h8;
+        *reinterpret_cast<uint32_t*>(p8 + 64) = l8;
+      } else {
+        uint2 h, l;
+        split2(o0, o1, h.x, l.x);
+        split2(o2, o3, h.y, l.y);
+        *reinterpret_cast<uint2*>(out_hi + row * C + c0) = h;
+        *reinterpret_cast<uint2*>(out_lo + row * C + c0) = l;
+      }
     }
 }
 
 void launch_ln_split(const float* src, const float* gamma, const float* beta, float eps,
-                     bf16* out_hi, bf16* out_lo, long long rows, int C, cudaStream_t s) {
+                     bf16* out_hi, bf16* out_lo, long long rows, int C, cudaStream_t s, int fmt8) {
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
-  launch_pdl(ln_split_kernel, dim3(blocks), dim3(256), 0, s, src, gamma, beta, eps, out_hi, out_lo, rows, C);
+  launch_pdl(ln_split_kernel, dim3(blocks), dim3(256), 0, s, src, gamma, beta, eps, out_hi, out_lo, rows, C, fmt8);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -47,8 +47,9 @@ struct ActSplitArgs {
 void launch_act_split(const ActSplitArgs& a, cudaStream_t s);
 
 // LayerNorm over C (eps) + affine -> split bf16 [rows, C]; C multiple of 128, <= 512
+// fmt8 = 1: the output is an f16f8 operand (out_hi = fp16, out_lo = fp8 rows; common.cuh)
 void launch_ln_split(const float* src, const float* gamma, const float* beta, float eps,
-                     bf16* out_hi, bf16* out_lo, long long rows, int C, cudaStream_t s);
+                     bf16* out_hi, bf16* out_lo, long long rows, int C, cudaStream_t s, int fmt8 = 0);
 // GeGLU: in [rows, 2F] -> split(in[:, :F] * gelu_erf(in[:, F:])) [rows, F]
 void launch_geglu_split(const float* src, bf16* out_hi, bf16* out_lo, long long rows, int F,
                         cudaStream_t s);

@@ -544,13 +544,13 @@ struct Builder {
     return s;
   }
 
-  Split ln_split(const float* src, long long rows, int C, const std::string& prefix) {
+  Split ln_split(const float* src, long long rows, int C, const std::string& prefix, bool f8 = false) {
     PF_CHECK(C % 128 == 0 && C <= 512, "LayerNorm width %d unsupported", C);
     Split s = alloc_split(static_cast<size_t>(rows) * C);
     Op& op = push(OP_LN_SPLIT);
     op.p[0] = src; op.p[1] = F(m, prefix + ".weight"); op.p[2] = F(m, prefix + ".bias");
     op.o[0] = s.hi; op.o[1] = s.lo;
-    op.i[0] = rows; op.i[1] = C;
+    op.i[0] = rows; op.i[1] = C; op.i[2] = f8 ? 1 : 0;
     op.f = 1e-5f;
     return s;
   }
@@ -775,7 +775,11 @@ struct Builder {
     // 1x1 skip conv (cin != cout): its operand is the PLAIN input.  With a RAW segment the second GEMM reads
     // the fp32 input tensors directly and converts them in shared memory (gemm_tc.cu); otherwise the
     // transform below writes a second, un-normalised operand in the same pass.
-    static const bool raw_skip_on = !(std::getenv("PF_RAW_SKIP") && std::atoi(std::getenv("PF_RAW_SKIP")) == 0);
+    // Measured on B200 (profiles/r4*): the dual transforms shrink by 0.5 ms per step, but the second GEMMs
+    // lose 0.9 ms (each raw k-block is a pipeline bubble of 0.6 - 1.1 us: TMA latency + conversion exceed the
+    // look-ahead of a 3-4 stage ring, and the 512-thread kernel caps the epilogue at 128 registers), so the
+    // RAW skip segment is opt-in: PF_RAW_SKIP=1.
+    static const bool raw_skip_on = std::getenv("PF_RAW_SKIP") && std::atoi(std::getenv("PF_RAW_SKIP")) != 0;
     const bool raw_skip = L.cin != L.cout && raw_skip_on && x0.p && (!x1 || x1->p) && x0.C % 64 == 0 &&
                           (!x1 || x1->C % 64 == 0) &&
                           raw_variant_ok(f8, 1, true, H, Wd, L.cout, 0, !split_only, split_only ? (f8_up ? 5 : 2) : 1);
@@ -954,14 +958,27 @@ struct Builder {
     const int sti = st_index++;
     const int Fh = 4 * C;
     const int bn_geglu = (2 * Fh) % 256 == 0 ? 256 : choose_bn(2 * Fh);
-    // RAW operands (gemm_tc.cu): GroupNorm -> proj_in and LayerNorm -> q/k/v, to_q (cross), GeGLU projection are
-    // applied by the consumer GEMM's conversion warps to the fp32 tensor; the LayerNorm row statistics come from
-    // the producing GEMM's epilogue.  PF_RAW_GN=0 / PF_RAW_LN=0 restore the separate transform passes.
+    // RAW operands (gemm_tc.cu): GroupNorm -> proj_in and LayerNorm -> q/k/v, to_q (cross), GeGLU projection can
+    // be applied by the consumer GEMM's conversion warps to the fp32 tensor; the LayerNorm row statistics then
+    // come from the producing GEMM's epilogue.  Measured on B200 (profiles/r4*, bench with the whole-step graph):
+    // GroupNorm -> proj_in is neutral in time (18.13 ms per step either way) and saves the operand round trip
+    // (11 transforms, 1.7 GB of DRAM traffic per step), so it is on (PF_RAW_GN=0 disables); the LayerNorm form
+    // is 0.6 ms SLOWER (the projections are bound by their epilogues, which the 512-thread kernel caps at 128
+    // registers, and every N tile converts the A tile again: 4x for q|k, 8x for GeGLU), so it is opt-in
+    // (PF_RAW_LN=1).
     static const bool raw_gn_on = !(std::getenv("PF_RAW_GN") && std::atoi(std::getenv("PF_RAW_GN")) == 0);
-    static const bool raw_ln_on = !(std::getenv("PF_RAW_LN") && std::atoi(std::getenv("PF_RAW_LN")) == 0);
+    static const bool raw_ln_on = std::getenv("PF_RAW_LN") && std::atoi(std::getenv("PF_RAW_LN")) != 0;
     const bool ln_qkv = raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, 2 * C, 0, false, 2) &&
                         raw_variant_ok(false, 0, false, H, Wd, C, 0, false, 3);
-    const bool ln_ff = raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, 2 * Fh, bn_geglu, false, 4);
+    // PF_FF_F8=1: feed-forward GEMMs (GeGLU projection, FF-out) on f16f8 operands, 2 tensor-time units per
+    // product instead of 3 (common.cuh).  Precision is fine (CPU emulation with every linear in f16f8,
+    // tools/experiments/precision_emul.py: max |err| 5.4e-5 against 5.9e-5 with the convolutions alone; on the
+    // GPU 5.0e-5 vs 4.7e-5), but it is SLOWER on B200 (profiles/r4g_*): the GeGLU projection needs 128-wide
+    // f16f8 tiles (two accumulators per tile) and is then bound by its GELU epilogue, 231 us vs 171 us with
+    // 256-wide split-bf16 tiles at 32 x 32; FF-out gains 4 us.  Off by default.
+    static const bool ff_f8_on = std::getenv("PF_FF_F8") && std::atoi(std::getenv("PF_FF_F8")) != 0;
+    const bool ff_f8 = ff_f8_on && pick_gemm(true, 0, true, H, Wd, 2 * Fh, 128, false).two;
+    const bool ln_ff = !ff_f8 && raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, 2 * Fh, bn_geglu, false, 4);
     const bool ln_q2 = raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, C, 0, false, 2);
     const bool raw_gn = raw_gn_on && x.p && raw_variant_ok(false, 0, false, H, Wd, C, 0, true, ln_qkv ? 6 : 0);
     float* t0 = alloc<float>(rows * C);
@@ -1135,12 +1152,23 @@ struct Builder {
       {
         // GeGLU fused into the projection's epilogue: weight rows are interleaved so every BN-wide
         // tile holds [BN/2 value | BN/2 gate] columns of the same output features
-        const int bn = bn_geglu;
-        ASrc s = ln_operand(xattn, rs_attn, tb + ".norm3", l3);
+        const int bn = ff_f8 ? 128 : bn_geglu;
+        if (m->packing) {  // both operand schemes are packed: a plan without CTA pairs falls back to split-bf16
+          W(m, tb + ".ff.net.0.proj.weight:geglu" + std::to_string(bn_geglu / 2), {tb + ".ff.net.0.proj.weight"}, bn_geglu / 2);
+          W(m, tb + ".ff.net.2.weight", {tb + ".ff.net.2.weight"});
+        }
+        ASrc s{Split(), C, Wd, H, B, 0};
+        if (ff_f8) {
+          l3 = ln_split(xattn, rows, C, tb + ".norm3", true);
+          s.buf = l3;
+          s.f8 = true;
+        } else {
+          s = ln_operand(xattn, rs_attn, tb + ".norm3", l3);
+        }
         Op& op = conv_gemm(s, W(m, tb + ".ff.net.0.proj.weight:geglu" + std::to_string(bn / 2),
-                                {tb + ".ff.net.0.proj.weight"}, bn / 2),
+                                {tb + ".ff.net.0.proj.weight"}, bn / 2, ff_f8),
                            nullptr, nullptr, H, Wd, 2 * Fh, 0, bn);
-        op.g.mode = OUT_GEGLU;
+        op.g.mode = ff_f8 ? OUT_GEGLU8 : OUT_GEGLU;
         op.g.out_hi = e.hi; op.g.out_lo = e.lo; op.g.ldc = Fh;
         op.g.addvec = F(m, tb + ".ff.net.0.proj.bias");
         op.g.addvec_ld = 0;
@@ -1150,8 +1178,8 @@ struct Builder {
       const bool last = (li + 1 == c.tf_layers);
       float* x3 = nullptr;
       {
-        ASrc s{e, Fh, Wd, H, B, 0};
-        Op& op = conv_gemm(s, W(m, tb + ".ff.net.2.weight", {tb + ".ff.net.2.weight"}), nullptr,
+        ASrc s{e, Fh, Wd, H, B, 0, ff_f8};
+        Op& op = conv_gemm(s, W(m, tb + ".ff.net.2.weight", {tb + ".ff.net.2.weight"}, 0, ff_f8), nullptr,
                            nullptr, H, Wd, C, 0, 0, !last);
         if (last) {
           // the last block's output feeds only proj_out: emit its split operand from the epilogue
@@ -1160,7 +1188,7 @@ struct Builder {
         } else {
           x3 = alloc<float>(rows * C);
           out_f32(op, x3, C, F(m, tb + ".ff.net.2.bias"), 0, xattn, C);
-          rs_t0 = ln_qkv ? new_rowstats(rows) : nullptr;
+          rs_t0 = (ln_qkv && !ff_f8) ? new_rowstats(rows) : nullptr;  // (no row-statistics f16f8 kernel)
           op.g.rowstats = rs_t0;
         }
       }
@@ -1683,7 +1711,7 @@ static void run_plan(pf_unet* m, Plan& plan, const float* x, const int64_t* t, c
       case OP_LN_SPLIT:
         launch_ln_split(static_cast<const float*>(op.p[0]), static_cast<const float*>(op.p[1]),
                         static_cast<const float*>(op.p[2]), op.f, static_cast<bf16*>(op.o[0]),
-                        static_cast<bf16*>(op.o[1]), op.i[0], (int)op.i[1], s);
+                        static_cast<bf16*>(op.o[1]), op.i[0], (int)op.i[1], s, (int)op.i[2]);
         break;
       case OP_GEGLU:
         launch_geglu_split(static_cast<const float*>(op.p[0]), static_cast<bf16*>(op.o[0]),
