@@ -417,7 +417,9 @@ def run_gpu_arm(args):
             "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16+f8 convolutions (fp16 product + e4m3 cross terms), bf16x3 linears/attention; fp32 accumulate",
+            "dtype": ("NON-PARITY fast mode: single fp16 / bf16 product per GEMM (attention still bf16x3); fp32 accumulate"
+                      if os.environ.get("PF_FAST") == "1" else
+                      "f16+f8 convolutions (fp16 product + e4m3 cross terms), bf16x3 linears/attention; fp32 accumulate"),
             "data": "synthetic",
             "config": {
                 "workload": cfg["workload"], "batch_per_gpu": B, "global_batch": world * B,
@@ -484,7 +486,12 @@ def main():
                     help="BASELINE.json configs[N]; 1 (default) is the configuration the metric is quoted on")
     ap.add_argument("--sustain-seconds", type=float, default=3.0,
                     help="length of the extra back-to-back run reported under `sustained` (0 = skip)")
+    ap.add_argument("--fast", action="store_true",
+                    help="NON-PARITY single-pass tensor math (PF_FAST=1): every GEMM issues only its hi x hi product; "
+                         "reported separately (BASELINE.md section 2), never the headline line")
     args = ap.parse_args()
+    if args.fast:
+        os.environ["PF_FAST"] = "1"  # read once by libpf_b200.so when the first plan is built
     if args.impl == "reference":
         run_reference_arm(args)
     else:

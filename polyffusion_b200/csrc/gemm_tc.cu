@@ -290,7 +290,11 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 for (int k = 0; k < GEMM_BK / 16; ++k) {
                   const uint64_t ko = static_cast<uint64_t>(k * 2);  // 32 B per K=16 step (16 B units)
                   const uint32_t accum = (kbi | j | k) != 0;
-                  if (F8) {
+                  if (p.fast) {
+                    // single-pass mode: hi x hi only, plain accumulator layout (N = BN)
+                    if (TWO) umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC, accum);
+                    else umma_bf16(acc, da_hi + ko, db_hi + ko, IDESC, accum);
+                  } else if (F8) {
                     // fp16 x fp16 (K = 16) and e4m3 x e4m3 (K = 32): 32 bytes of the row each
                     if (TWO) {
                       umma2_bf16(acc, da_hi + ko, db_hi + ko, IDESC, accum);
@@ -512,6 +516,11 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * ACC_COLS);
       // logical accumulator columns [c, c + 32) of this warp's 32 rows (wait included)
       auto ld_acc = [&](int c, uint32_t (&v)[32]) {
+        if (p.fast) {
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          return;
+        }
         if constexpr (F8) {
           uint32_t w[32];
           tmem_ld32(taddr + c, v);

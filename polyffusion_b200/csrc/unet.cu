@@ -614,6 +614,8 @@ struct Builder {
     // cta_group::2 (CTA pairs, 256-row tile pairs) whenever the M tiles pair up
     k.two = !one_cta && ((B * tiles_per_img) % 2 == 0);
     k.bn = bn_override ? bn_override : (f8 && f8_bn256 && k.two && Cout % 256 == 0) ? 256 : choose_bn(Cout);
+    // (256-wide tiles for the small-M linears at 16 x 16 -- one wave of 64 tile pairs instead of 1.73 waves of
+    // 128-wide ones -- measured no faster: 24.3 vs 23.5 us per launch, profiles/r4k_*)
     PF_CHECK(!f8 || k.bn <= 128 || k.two, "f16f8 GEMM: BN=%d needs CTA pairs", k.bn);
     k.stack = !f8 && k.two && k.bn <= 128 && (stack_sel < 0 || stack_sel == k.bn);
     k.halo = halo_ok && f32_out && k.two && (k.stack || f8) && k.bn == 64 && k.box_w == 128 && k.box_h == 1 &&
@@ -718,6 +720,10 @@ struct Builder {
     g.raw = (a0.raw0 || (a1 && a1->raw0)) ? 1 : 0;
     static const int raw_dbg = std::getenv("PF_RAW_DBG") ? std::atoi(std::getenv("PF_RAW_DBG")) : 0;
     g.raw_dbg = raw_dbg;
+    // PF_FAST=1: single-pass tensor math (BASELINE.md section 2 asks for both figures).  NOT a parity mode:
+    // every GEMM issues only its hi x hi product; the attention kernel and every non-GEMM kernel are unchanged.
+    static const bool fast = std::getenv("PF_FAST") && std::atoi(std::getenv("PF_FAST")) != 0;
+    g.fast = fast ? 1 : 0;
     PF_CHECK(!g.raw || two, "RAW GEMM segments need CTA pairs");
     fill_seg(g.seg[0], a0, w0, two ? bn / 2 : bn, box_w, box_h, halo);
     g.seg[0].b_row0 = row0;
