@@ -382,10 +382,6 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           raw_bits ^= 1u << stage;
           uint8_t* a0 = gsm + stage * STAGE_BYTES;
           float4 va[8], vb[8];
-          if (p.raw_dbg & 2) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) va[i] = vb[i] = make_float4(1.f, 2.f, 3.f, 4.f);
-          } else
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4* rp = reinterpret_cast<const float4*>(a0 + (i * 16 + r0) * 256 + j * 16);
@@ -419,7 +415,6 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
               vb[i].z = fmaf(vb[i].z, scb.z, shb.z); vb[i].w = fmaf(vb[i].w, scb.w, shb.w);
             }
           }
-          if (!(p.raw_dbg & 1))
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int prow = i * 16 + r0;
@@ -454,7 +449,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           // reads this CTA's A tile (the leader only issues the instruction).  The .shared::cta form is a
           // FENCE.VIEW.ASYNC; the unqualified fence and a cluster-scope release arrive both lower to
           // MEMBAR.ALL.GPU, which cost ~0.7 us per k-block here.
-          if (!(p.raw_dbg & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(smem_u32(&conv_full[stage]));
           if (aff) {
@@ -641,6 +636,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
               if (has_res) {
                 o.x += rres[it].x; o.y += rres[it].y; o.z += rres[it].z; o.w += rres[it].w;
               }
+              // (st.global.cs / .cg hints measured: no change, profiles/r4m_*; without these stores the GEMMs of
+              // a step take 1.75 ms less, about the HBM time of the 7.4 GB they write, profiles/r4l_*)
               *reinterpret_cast<float4*>(p.out + zoff + m * p.ldc + tc.n0 + c + c4) = o;
               if constexpr (STATS == 1) {
                 ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
@@ -994,16 +991,7 @@ cudaError_t launch_gemm(const GemmParams& p, int bn, int num_ctas, cudaStream_t 
   GemmKernel k = pick_kernel(bn, kind, v, p.raw != 0);
   if (!k) return cudaErrorInvalidValue;
   if (p.raw && !p.two_cta) return cudaErrorInvalidValue;
-  bool raw_kernel = p.raw != 0;
-  // (timing experiment) PF_RAW_FORCE=1: run launches without raw segments on the 512-thread RAW kernels too
-  static const bool raw_force = std::getenv("PF_RAW_FORCE") != nullptr;
-  if (raw_force && !raw_kernel && p.two_cta) {
-    GemmKernel kr = pick_kernel(bn, kind, v, true);
-    if (kr) {
-      k = kr;
-      raw_kernel = true;
-    }
-  }
+  const bool raw_kernel = p.raw != 0;
   const int nthreads = raw_kernel ? GEMM_RAW_THREADS : GEMM_THREADS;
   if (p.two_cta) {
     const int smem = p.nstages * (p.halo ? gemm_stage_bytes2_halo(bn) : gemm_stage_bytes2(bn)) + 1024 +

@@ -92,7 +92,6 @@ struct alignas(64) GemmParams {
   int f8;               // 1: f16f8 operands (a_hi/b_hi = fp16 maps, a_lo/b_lo = byte maps of the fp8 rows)
   int fast;             // 1: NON-PARITY single-pass mode (PF_FAST=1, reported separately): only the hi x hi product
                         // is issued (fp16 x fp16 for f16f8 operands, bf16 x bf16 for split-bf16 ones)
-  int raw_dbg;          // (timing experiments only: skip parts of the conversion, results are garbage)
   int raw;              // 1: at least one segment is RAW (512-thread kernel with conversion warps; two_cta only)
   // nearest-2x-upsample + conv3x3 evaluated as four 2x2 parity convolutions at LOW resolution:
   // OUT_F32 rows are scattered to pixel (2y + up_py, 2x + up_px) of the [img][2H][2W] output

@@ -136,6 +136,16 @@ namespace pf {
 
 static thread_local std::string g_err;
 
+// device scratch released on every exit path (entry points that must allocate: once-per-call helpers, never the
+// launch path of a forward)
+struct DevBuf {
+  void* p = nullptr;
+  explicit DevBuf(size_t bytes) { PF_CUDA(cudaMalloc(&p, bytes ? bytes : 4)); }
+  ~DevBuf() { cudaFree(p); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
 template <class F>
 static int guarded(F&& f) {
   try {
@@ -718,8 +728,6 @@ struct Builder {
     g.stack = pk.stack ? 1 : 0;
     g.halo = halo ? 1 : 0;
     g.raw = (a0.raw0 || (a1 && a1->raw0)) ? 1 : 0;
-    static const int raw_dbg = std::getenv("PF_RAW_DBG") ? std::atoi(std::getenv("PF_RAW_DBG")) : 0;
-    g.raw_dbg = raw_dbg;
     // PF_FAST=1: single-pass tensor math (BASELINE.md section 2 asks for both figures).  NOT a parity mode:
     // every GEMM issues only its hi x hi product; the attention kernel and every non-GEMM kernel are unchanged.
     static const bool fast = std::getenv("PF_FAST") && std::atoi(std::getenv("PF_FAST")) != 0;
@@ -1952,10 +1960,9 @@ int pf_unet_enable_time_lut(pf_unet* h, int32_t n_steps, pf_stream stream) {
     h->plans.clear();
     h->last_plan = nullptr;
     const size_t ws_bytes = static_cast<size_t>(n_steps) * (h->cfg.channels * 9 + h->emb_total) * sizeof(float) + (1 << 20);
-    char* ws = nullptr;
-    long long* tt = nullptr;
-    PF_CUDA(cudaMalloc(&ws, ws_bytes));
-    PF_CUDA(cudaMalloc(&tt, n_steps * sizeof(long long)));
+    DevBuf ws_buf(ws_bytes), tt_buf(n_steps * sizeof(long long));
+    char* ws = static_cast<char*>(ws_buf.p);
+    long long* tt = static_cast<long long*>(tt_buf.p);
     std::vector<long long> host(n_steps);
     for (int i = 0; i < n_steps; ++i) host[i] = i;
     PF_CUDA(cudaMemcpyAsync(tt, host.data(), n_steps * sizeof(long long), cudaMemcpyHostToDevice, s));
@@ -1967,8 +1974,6 @@ int pf_unet_enable_time_lut(pf_unet* h, int32_t n_steps, pf_stream stream) {
     PF_CUDA(cudaMemcpyAsync(lut, ea, static_cast<size_t>(n_steps) * h->emb_total * sizeof(float),
                             cudaMemcpyDeviceToDevice, s));
     PF_CUDA(cudaStreamSynchronize(s));
-    cudaFree(ws);
-    cudaFree(tt);
     h->time_lut = lut;
     h->time_lut_rows = n_steps;
   });
@@ -2131,15 +2136,14 @@ int pf_get_mask(const float* orig, float* mask, int32_t n_seg, int32_t seg_per_s
     PF_CHECK(orig && mask && n_seg > 0 && seg_per_song > 0 && n_seg % seg_per_song == 0,
              "bad get_mask arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int* scratch = nullptr;
-    PF_CUDA(cudaMalloc(&scratch, (static_cast<size_t>(n_seg) * steps + 1) * sizeof(int)));
+    DevBuf buf((static_cast<size_t>(n_seg) * steps + 1) * sizeof(int));
+    int* scratch = static_cast<int*>(buf.p);
     int* err = scratch + static_cast<size_t>(n_seg) * steps;
     PF_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
     launch_get_mask(orig, mask, scratch, err, n_seg, seg_per_song, channels, steps, pitches, above, s);
     int herr = 0;
     PF_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
     PF_CUDA(cudaStreamSynchronize(s));
-    cudaFree(scratch);
     PF_CHECK(herr == 0, "get_mask: a song has no onset at all (the reference raises IndexError here)");
   });
 }
