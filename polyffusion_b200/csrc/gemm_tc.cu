@@ -539,24 +539,33 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         }
       };
 
-      if constexpr (MODE == OUT_SPLIT_T) {
-        // [img][n][token]; consecutive lanes -> consecutive tokens (already coalesced)
-        const long long tok = static_cast<long long>(tc.trem) * GEMM_BM + q * 32 + lane;
-        const long long base = zoff + static_cast<long long>(tc.img) * p.out_img + tok;
+      // OUT_QKV: the tile's column range decides between the row-major and the transposed store
+      const bool transposed = MODE == OUT_SPLIT_T || (MODE == OUT_QKV && tc.n0 >= p.qkv_split);
+      if (transposed) {
+        if constexpr (MODE == OUT_SPLIT_T || MODE == OUT_QKV) {
+          // [img][n][token]; consecutive lanes -> consecutive tokens (already coalesced)
+          __nv_bfloat16* th = MODE == OUT_QKV ? p.out2_hi : p.out_hi;
+          __nv_bfloat16* tl = MODE == OUT_QKV ? p.out2_lo : p.out_lo;
+          const long long tld = MODE == OUT_QKV ? p.ldc2 : p.ldc;
+          const long long timg = MODE == OUT_QKV ? p.out_img2 : p.out_img;
+          const int tn0 = MODE == OUT_QKV ? tc.n0 - p.qkv_split : tc.n0;
+          const long long tok = static_cast<long long>(tc.trem) * GEMM_BM + q * 32 + lane;
+          const long long base = zoff + static_cast<long long>(tc.img) * timg + tok;
 #pragma unroll 1
-        for (int c = chalf * 32; c < BN; c += 64) {
-          uint32_t v[32];
-          ld_acc(c, v);
+          for (int c = chalf * 32; c < BN; c += 64) {
+            uint32_t v[32];
+            ld_acc(c, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            __nv_bfloat16 h, l;
-            split_bf16(__uint_as_float(v[j]), h, l);
-            const long long o = base + static_cast<long long>(tc.n0 + c + j) * p.ldc;
-            p.out_hi[o] = h;
-            p.out_lo[o] = l;
+            for (int j = 0; j < 32; ++j) {
+              __nv_bfloat16 h, l;
+              split_bf16(__uint_as_float(v[j]), h, l);
+              const long long o = base + static_cast<long long>(tn0 + c + j) * tld;
+              th[o] = h;
+              tl[o] = l;
+            }
           }
         }
-      } else {
+      } else if constexpr (MODE != OUT_SPLIT_T) {
         constexpr bool geglu = (MODE == OUT_GEGLU || MODE == OUT_GEGLU8);
         const int ncols = geglu ? BN / 2 : BN;          // output columns produced by this tile
         const int ocol0 = geglu ? (tc.n0 / 2) : tc.n0;  // first output column
@@ -845,6 +854,7 @@ static GemmKernel pick_variant(int v) {
       case 3: return gemm_tc2s_kernel<BN, OUT_SPLIT_T, false>;
       case 5: return gemm_tc2s_kernel<BN, OUT_SPLIT8, false>;
       case 6: return gemm_tc2s_kernel<BN, OUT_F32, 2>;
+      case 8: return gemm_tc2s_kernel<BN, OUT_QKV, false>;
       case 4: return gemm_tc2s_kernel<BN, OUT_GEGLU, false>;
       default: return nullptr;
     }
@@ -956,7 +966,7 @@ static GemmKernel pick_kernel(int bn, int kind, int v, bool raw = false) {
 cudaError_t gemm_init_attrs() {
   for (int bn : {64, 128, 256})
     for (int kind = 0; kind < 7; ++kind)
-      for (int v = 0; v < 8; ++v)
+      for (int v = 0; v < 9; ++v)
         for (int raw = 0; raw < 2; ++raw) {
           GemmKernel k = pick_kernel(bn, kind, v, raw != 0);
           if (!k) continue;
@@ -978,6 +988,7 @@ static int gemm_variant(const GemmParams& p) {
     case OUT_SPLIT_T: return 3;
     case OUT_SPLIT8: return 5;
     case OUT_GEGLU8: return 7;
+    case OUT_QKV: return 8;
     default: return 4;
   }
 }

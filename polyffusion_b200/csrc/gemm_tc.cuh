@@ -33,6 +33,8 @@ enum GemmOutMode : int {
   OUT_SPLIT8 = 4,     // f16f8 activation operand of (acc + addvec + resid): out_hi = fp16 [m, ldc],
                       // out_lo = fp8 rows [m][ldc / 64][h8 x 64 | l8 x 64] (common.cuh)
   OUT_GEGLU8 = 5,     // OUT_GEGLU with the result stored as an f16f8 activation operand
+  OUT_QKV = 6,        // fused q|k|v projection: N tiles below qkv_split -> OUT_SPLIT into out_hi/lo (q|k rows),
+                      // tiles from qkv_split on -> OUT_SPLIT_T into out2_hi/lo (V^T, the P V operand)
 };
 
 struct alignas(64) GemmSeg {
@@ -78,6 +80,10 @@ struct alignas(64) GemmParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   long long ldc, out_zb, out_zh, out_img;
+  __nv_bfloat16* out2_hi;  // OUT_QKV: transposed part [img][n - qkv_split][token], row stride ldc2, image stride out_img2
+  __nv_bfloat16* out2_lo;
+  long long ldc2, out_img2;
+  int qkv_split, pad2;
   const float* addvec;  // [img, addvec_ld] or null
   const float* resid;   // [m, ldr] or null
   long long addvec_ld, ldr;

@@ -1061,13 +1061,33 @@ struct Builder {
       {
         PackedW& w = W(m, tb + ".attn1.qkv", {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight",
                                              tb + ".attn1.to_v.weight"});
-        Op& op = conv_gemm(sl, w, nullptr, nullptr, H, Wd, 2 * C, 0);
-        op.g.mode = OUT_SPLIT;
-        op.g.out_hi = qk.hi; op.g.out_lo = qk.lo; op.g.ldc = 2 * C;
-        Op& ov = conv_gemm(sl, w, nullptr, nullptr, H, Wd, C, 2 * C);
-        ov.g.mode = OUT_SPLIT_T;
-        ov.g.out_hi = vt.hi; ov.g.out_lo = vt.lo; ov.g.ldc = N;
-        ov.g.out_img = static_cast<long long>(C) * N;
+        // q | k | v in ONE launch (OUT_QKV: the V tiles are stored transposed, as the P V operand) when the
+        // kernel family has the variant; otherwise a q|k launch and a V launch.  PF_QKV_FUSED=0 disables.
+        static const bool qkv_fused_on = !(std::getenv("PF_QKV_FUSED") && std::atoi(std::getenv("PF_QKV_FUSED")) == 0);
+        bool fused = false;
+        if (qkv_fused_on && !sl.raw0) {
+          const GemmPick pk = pick_gemm(false, 0, true, H, Wd, 3 * C, 0, false);
+          GemmParams probe;
+          memset(&probe, 0, sizeof probe);
+          probe.two_cta = pk.two; probe.stack = pk.stack; probe.mode = OUT_QKV;
+          fused = (2 * C) % pk.bn == 0 && gemm_kernel_available(probe, pk.bn);
+        }
+        if (fused) {
+          Op& op = conv_gemm(sl, w, nullptr, nullptr, H, Wd, 3 * C, 0, 0, false);
+          op.g.mode = OUT_QKV;
+          op.g.out_hi = qk.hi; op.g.out_lo = qk.lo; op.g.ldc = 2 * C;
+          op.g.out2_hi = vt.hi; op.g.out2_lo = vt.lo; op.g.ldc2 = N;
+          op.g.out_img2 = static_cast<long long>(C) * N;
+          op.g.qkv_split = 2 * C;
+        } else {
+          Op& op = conv_gemm(sl, w, nullptr, nullptr, H, Wd, 2 * C, 0);
+          op.g.mode = OUT_SPLIT;
+          op.g.out_hi = qk.hi; op.g.out_lo = qk.lo; op.g.ldc = 2 * C;
+          Op& ov = conv_gemm(sl, w, nullptr, nullptr, H, Wd, C, 2 * C);
+          ov.g.mode = OUT_SPLIT_T;
+          ov.g.out_hi = vt.hi; ov.g.out_lo = vt.lo; ov.g.ldc = N;
+          ov.g.out_img = static_cast<long long>(C) * N;
+        }
       }
       free_split(l1);
       Split o = alloc_split(rows * C);

@@ -8,6 +8,7 @@ rtol 1e-3 / atol 1e-4.
   PF_RAW_LN=1     LayerNorm -> q/k/v / GeGLU through the conversion warps, row statistics from GEMM epilogues
   PF_FF_F8=1      feed-forward GEMMs on f16f8 operands (GeGLU epilogue writing an f16f8 operand)
   PF_CONV_F8_MAX_HW=0  split-bf16 convolutions everywhere
+  PF_QKV_FUSED=0  separate q|k and V projection launches instead of the fused OUT_QKV launch
 """
 import os
 import re
@@ -27,6 +28,7 @@ CASES = [
     {"PF_RAW_SKIP": "1", "PF_RAW_LN": "1"},
     {"PF_FF_F8": "1"},
     {"PF_CONV_F8_MAX_HW": "0", "PF_RAW_LN": "1"},
+    {"PF_QKV_FUSED": "0"},
 ]
 
 
