@@ -60,15 +60,22 @@ def load_peaks():
 
 
 def load_gemm_traffic():
-    """DRAM bytes moved by the tcgen05 GEMM launches of ONE step, from the newest committed ncu launch
-    list (profiles/*_gemm_traffic.json, written by tools/ncu_launches_step.py); None if absent."""
+    """DRAM bytes moved by the tcgen05 GEMM launches of ONE step, from a committed ncu launch list
+    (profiles/*_gemm_traffic.json, written by tools/ncu_launches_step.py): the file captured at the current
+    kernel sources when there is one (file times mean nothing after a checkout), else the last by name
+    (reported as stale by the caller); None if absent."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")), key=os.path.getmtime)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")))
     if not files:
         return None, None, None
-    with open(files[-1]) as f:
-        d = json.load(f)
-    return (d["gemm_dram_bytes_read"] + d["gemm_dram_bytes_write"], os.path.relpath(files[-1], ROOT),
+    docs = []
+    for path in files:
+        with open(path) as f:
+            docs.append((path, json.load(f)))
+    cur = kernel_source_hash()
+    match = [pd for pd in docs if pd[1].get("kernel_source_hash") == cur]
+    path, d = (match or docs)[-1]
+    return (d["gemm_dram_bytes_read"] + d["gemm_dram_bytes_write"], os.path.relpath(path, ROOT),
             d.get("kernel_source_hash"))
 
 
