@@ -356,10 +356,9 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
   const int HW = a.H * a.W;
   const int items = HW * c16n;
   const long long pix_base = static_cast<long long>(b) * HW;
+  // grid-stride over the sample's items: gridDim.x blocks per sample, one GroupNorm prologue per block
 #pragma unroll 1
-  for (int k = 0; k < AS_IPT; ++k) {
-    const int item = (blockIdx.x * AS_IPT + k) * blockDim.x + threadIdx.x;
-    if (item >= items) break;
+  for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < items; item += gridDim.x * blockDim.x) {
     const int c = (item % c16n) * 16;
     const int pl = item / c16n;  // pixel inside the sample
     const long long pix = pix_base + pl;
@@ -419,7 +418,20 @@ void launch_act_split(const ActSplitArgs& a, cudaStream_t s) {
   // Measured alternatives on B200, batch 64 (profiles/r4i_*, r4j_*; sum over the 47 transforms of one step):
   // 1 / 2 / 8 items per thread 4.76 / 4.27 / 4.17 ms against 3.98 ms with 4; issuing the loads of item k + 1
   // before item k is processed (77 registers, 3 blocks per SM, or capped at 64 registers for 4) 4.31 / 4.11 ms.
-  dim3 grid(static_cast<unsigned>((items + threads * AS_IPT - 1) / (threads * AS_IPT)), a.B);
+  // Normalising transforms run in the persistent form: ONE resident wave of blocks in total (4 blocks of 256
+  // threads per SM), each block striding over its sample's items -- the GroupNorm prologue is paid once per block
+  // and there is no partial last wave (measured on B200, batch 64, profiles/r4o_*: 103 -> 98.5 us on the 128 x 128
+  // maps, 74 -> 70.5 us at 64 x 64, 44 -> 40 us at 32 x 32; two / four waves gain less).  The plain re-layout
+  // transforms (no prologue) are slower that way (86 -> 98 us for the stride-2 planes) and keep one block per
+  // 4 items per thread.  PF_ACT_WAVES overrides (0 = never persistent).
+  static const int waves = std::getenv("PF_ACT_WAVES") ? std::atoi(std::getenv("PF_ACT_WAVES")) : 1;
+  long long bx = (items + threads * AS_IPT - 1) / (threads * AS_IPT);
+  if (waves > 0 && a.stats0 != nullptr) {
+    const long long slots = 148ll * (1024 / threads) * waves;
+    const long long per_sample = std::max(1ll, slots / a.B);
+    bx = std::min(bx, per_sample);
+  }
+  dim3 grid(static_cast<unsigned>(bx), a.B);
   launch_pdl(act_split_kernel, grid, dim3(threads), 0, s, a);
 }
 
