@@ -41,8 +41,8 @@ constexpr int AT_VS = 4;  // V ring stages
 constexpr int AT_KV_BYTES = 64 * 128;       // 64 rows x 64 bf16
 constexpr int AT_OFF_K = 0;                                   // [KS][hi, lo]
 constexpr int AT_OFF_V = AT_OFF_K + AT_KS * 2 * AT_KV_BYTES;  // [VS][hi, lo]
-constexpr int AT_OFF_X = AT_OFF_V + AT_VS * 2 * AT_KV_BYTES;  // float xch[2][128][4]
-constexpr int AT_SMEM = AT_OFF_X + 2 * 128 * 4 * 4;
+constexpr int AT_OFF_X = AT_OFF_V + AT_VS * 2 * AT_KV_BYTES;  // float xch[3][128][4]: row maxima, row sums (x2)
+constexpr int AT_SMEM = AT_OFF_X + 3 * 128 * 4 * 4;
 constexpr int AT_SB = 2;  // S/P buffers (key blocks in flight)
 constexpr uint32_t TM_O = 0, TM_S = 128, TM_Q = 384;
 
@@ -83,6 +83,19 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const int nqt = p.N / 128, nb = p.Nk / 64;
   const long long items = static_cast<long long>(p.B) * p.heads * nqt;
+  // Single-pass decision for (sample b, head h), identical in every role (plain global reads of values written by
+  // the previous kernel): |s_ij| <= |q_i| |k_j| <= Q_max K_max =: bound.  With the stabiliser m~ = bound every
+  // probability is exp2((s - bound) c) in [2^(-2 bound c), 1]; below 2^-96 that is safe in fp32 / bf16 (no
+  // underflow, and softmax is invariant to the shift), so pass 1 (the row maximum) is not needed.  Returns
+  // bound * c, or a negative value when two passes are required.
+  auto single_pass_mc = [&](int b, int h) -> float {
+    if (p.qknorm == nullptr) return -1.f;
+    const float* qn = p.qknorm + (static_cast<long long>(b) * 2 * p.heads + h) * 2;
+    const float* kn = qn + p.heads * 2;
+    const float q2 = __ldcg(qn) + __ldcg(qn + 1), k2 = __ldcg(kn) + __ldcg(kn + 1);
+    const float mc = sqrtf(q2 * k2) * 1.002f * p.scale_log2e;
+    return mc < 48.f ? mc : -1.f;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -122,7 +135,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
       for (long long w = blockIdx.x; w < items; w += gridDim.x) {
         const int bh = static_cast<int>(w / nqt);
         const int b = bh / p.heads, h = bh % p.heads;
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = single_pass_mc(b, h) >= 0.f ? 1 : 0; pass < 2; ++pass) {
           for (int j = 0; j < nb; ++j) {
             {
               const uint32_t st = kc % AT_KS, ph = (kc / AT_KS) & 1u;
@@ -183,7 +196,11 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
           ++kc;
           ++sc;
         };
-        for (int j = 0; j < nb; ++j) issue_s(false);  // pass 1
+        {
+          const int bh = static_cast<int>(w / nqt);
+          if (single_pass_mc(bh / p.heads, bh % p.heads) < 0.f)
+            for (int j = 0; j < nb; ++j) issue_s(false);  // pass 1
+        }
         const int pre = nb < AT_SB ? nb : AT_SB;
         const uint32_t sc2 = sc;                      // S counter of pass-2 block 0
         for (int j = 0; j < pre; ++j) issue_s(true);  // pass 2 runs two key blocks ahead of P V
@@ -222,7 +239,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
     const int q = warp & 3;
     const int part = (warp - 2) >> 2;  // 0..3: which 16 columns of a 64-column block
     const int row = q * 32 + lane;
-    float* xch = reinterpret_cast<float*>(gbase + AT_OFF_X);  // [2][128][4]
+    float* xch = reinterpret_cast<float*>(gbase + AT_OFF_X);  // [3][128][4]
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float c = p.scale_log2e;
     // Q row of work item w -> TMEM buffer (local item index & 1): part 0 stages hi, part 1 stages lo
@@ -257,26 +274,29 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
       const int b = bh / p.heads, h = bh % p.heads;
       if (it == 0) stage_q(w, 0);
       if (w + gridDim.x < items) stage_q(w + gridDim.x, it + 1);  // one work item ahead
-      // ---- pass 1: row maximum
-      float mx = -INFINITY;
-      for (int j = 0; j < nb; ++j, ++sc) {
-        const uint32_t sb = sc % AT_SB, sph = (sc / AT_SB) & 1u;
-        mbar_wait(smem_u32(&s_full[sb]), sph);
-        tc_fence_after();
-        uint32_t v[16];
-        tmem_ld16(lane_addr + TM_S + sb * 128 + part * 16, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_empty[sb]));
+      // ---- pass 1: row maximum (skipped when the norm bound is usable as the stabiliser)
+      float mc = single_pass_mc(b, h);
+      if (mc < 0.f) {
+        float mx = -INFINITY;
+        for (int j = 0; j < nb; ++j, ++sc) {
+          const uint32_t sb = sc % AT_SB, sph = (sc / AT_SB) & 1u;
+          mbar_wait(smem_u32(&s_full[sb]), sph);
+          tc_fence_after();
+          uint32_t v[16];
+          tmem_ld16(lane_addr + TM_S + sb * 128 + part * 16, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s_empty[sb]));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        xch[row * 4 + part] = mx;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float4 m4 = *reinterpret_cast<const float4*>(xch + row * 4);
+        const float m = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
+        mc = m * c;
       }
-      xch[row * 4 + part] = mx;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      const float4 m4 = *reinterpret_cast<const float4*>(xch + row * 4);
-      const float m = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
-      const float mc = m * c;
       // ---- pass 2: probabilities -> P (TMEM, over the S columns just read), row sums
       float sum = 0.f;
       for (int j = 0; j < nb; ++j, ++sc) {
@@ -309,9 +329,12 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
           mbar_arrive(smem_u32(&p_full[sb]));  // P_j lives in S buffer sb
         }
       }
-      xch[512 + row * 4 + part] = sum;
+      // the row sums alternate between two exchange buffers: without pass 1 there is only ONE block barrier per
+      // work item, and a fast warp must not overwrite sums a slow warp has not read yet
+      float* xs = xch + 512 + (it & 1u) * 512;
+      xs[row * 4 + part] = sum;
       asm volatile("bar.sync 1, 512;" ::: "memory");
-      const float4 l4 = *reinterpret_cast<const float4*>(xch + 512 + row * 4);
+      const float4 l4 = *reinterpret_cast<const float4*>(xs + row * 4);
       const float inv = 1.0f / ((l4.x + l4.y) + (l4.z + l4.w));
       // ---- epilogue: O / l -> split-bf16 [B*N, ldo] at columns h*64 + part*16
       mbar_wait(smem_u32(&o_full), it & 1u);

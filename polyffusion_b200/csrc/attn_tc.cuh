@@ -21,6 +21,11 @@ struct alignas(64) AttnParams {
   __nv_bfloat16* o_hi;     // split-bf16 output [B*N, ldo], head h at columns ocol0 + h*64
   __nv_bfloat16* o_lo;
   long long ldo;
+  // optional [B][2][heads][2] fp32: upper bounds of max_i |q_i|^2 and max_j |k_j|^2 per (sample, head), as two
+  // 32-column halves each (written with atomicMax by the q|k|v projection's epilogue, gemm_tc.cu OUT_QKV).  With
+  // it the kernel takes Q_max * K_max (Cauchy-Schwarz) as the softmax stabiliser and skips pass 1 whenever that
+  // bound is small enough for fp32 (see attn_tc.cu); null = always two passes
+  const float* qknorm;
 };
 
 int attn_smem_bytes();

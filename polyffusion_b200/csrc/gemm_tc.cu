@@ -591,6 +591,23 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           {
             uint32_t v[32];
             ld_acc(c, v);
+            if constexpr (MODE == OUT_QKV) {
+              // q / k tiles: bound of the largest squared row norm per (image, head, 32-column half) for the
+              // attention kernel's single-pass stabiliser
+              if (p.qknorm != nullptr) {
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ss = fmaf(__uint_as_float(v[j]), __uint_as_float(v[j]), ss);
+                const unsigned mxu = __reduce_max_sync(0xffffffffu, __float_as_uint(ss));
+                if (lane == 0) {
+                  const int cdim = p.qkv_split >> 1, col = tc.n0 + c;
+                  const int which = col / cdim, hc = col % cdim;
+                  unsigned* d = reinterpret_cast<unsigned*>(p.qknorm) +
+                                ((static_cast<long long>(tc.img) * 2 + which) * (cdim >> 6) + (hc >> 6)) * 2 + ((hc >> 5) & 1);
+                  atomicMax(d, mxu);
+                }
+              }
+            }
             if constexpr (geglu) {
               uint32_t g[32];
               ld_acc(BN / 2 + c, g);

@@ -84,6 +84,8 @@ struct alignas(64) GemmParams {
   __nv_bfloat16* out2_lo;
   long long ldc2, out_img2;
   int qkv_split, pad2;
+  float* qknorm;        // OUT_QKV (optional): [img][2 (q, k)][heads][2 halves] fp32, zero-initialised; receives
+                        // atomicMax of the 32-column partial squared norms of the q / k rows (attn_tc.cuh)
   const float* addvec;  // [img, addvec_ld] or null
   const float* resid;   // [m, ldr] or null
   long long addvec_ld, ldr;

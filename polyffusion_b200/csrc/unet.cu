@@ -852,7 +852,7 @@ struct Builder {
   // k ([B*Nk, ldk] split, cols kcol0 + h*64) and v^T ([B*heads*64, Nk] split) -> O split [B*N, ldo]
   void attention_core(const Split& q, int ldq, int qcol0, const Split& k, int ldk, int kcol0,
                       const Split& vt, int N, int Nq_w, int Nq_h, int Nk, int heads, Split& o,
-                      int ldo) {
+                      int ldo, const float* qknorm = nullptr) {
     const int Z = B * heads;
     static const bool unfused = std::getenv("PF_ATTN_UNFUSED") != nullptr;
     if (!unfused) {
@@ -871,6 +871,7 @@ struct Builder {
       a.qcol0 = qcol0; a.kcol0 = kcol0; a.ocol0 = 0;
       a.scale_log2e = 0.125f * 1.4426950408889634f;  // d_head ** -0.5 (unet_attention.py:157) * log2(e)
       a.o_hi = o.hi; a.o_lo = o.lo; a.ldo = ldo;
+      a.qknorm = qknorm;
       (void)Nq_w; (void)Nq_h;
       return;
     }
@@ -1058,6 +1059,7 @@ struct Builder {
       ASrc sl = ln_operand(t0, rs_t0, tb + ".norm1", l1);
       Split qk = alloc_split(rows * 2 * C);
       Split vt = alloc_split(rows * C);
+      float* qknorm = nullptr;
       {
         PackedW& w = W(m, tb + ".attn1.qkv", {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight",
                                              tb + ".attn1.to_v.weight"});
@@ -1073,8 +1075,13 @@ struct Builder {
           fused = (2 * C) % pk.bn == 0 && gemm_kernel_available(probe, pk.bn);
         }
         if (fused) {
+          // squared-norm bounds of the q / k rows per (sample, head): lets the attention kernel skip its
+          // row-maximum pass (attn_tc.cu).  PF_ATTN_1PASS=0 disables.
+          static const bool one_pass_on = !(std::getenv("PF_ATTN_1PASS") && std::atoi(std::getenv("PF_ATTN_1PASS")) == 0);
+          if (one_pass_on) qknorm = new_rowstats(static_cast<long long>(B) * heads * 2);
           Op& op = conv_gemm(sl, w, nullptr, nullptr, H, Wd, 3 * C, 0, 0, false);
           op.g.mode = OUT_QKV;
+          op.g.qknorm = qknorm;
           op.g.out_hi = qk.hi; op.g.out_lo = qk.lo; op.g.ldc = 2 * C;
           op.g.out2_hi = vt.hi; op.g.out2_lo = vt.lo; op.g.ldc2 = N;
           op.g.out_img2 = static_cast<long long>(C) * N;
@@ -1091,7 +1098,7 @@ struct Builder {
       }
       free_split(l1);
       Split o = alloc_split(rows * C);
-      attention_core(qk, 2 * C, 0, qk, 2 * C, C, vt, N, Wd, H, N, heads, o, C);
+      attention_core(qk, 2 * C, 0, qk, 2 * C, C, vt, N, Wd, H, N, heads, o, C, qknorm);
       free_split(qk);
       free_split(vt);
       float* x1 = alloc<float>(rows * C);
@@ -1356,7 +1363,8 @@ struct Builder {
         int h = H, w = Wd;
         auto walk = [&](const BlockSpec& b) {
           for (auto& l : b.layers) {
-            if (l.kind == Layer::ST) rfloats += static_cast<size_t>(3) * c.tf_layers * B * h * w * 2;
+            if (l.kind == Layer::ST)
+              rfloats += static_cast<size_t>(c.tf_layers) * (static_cast<size_t>(3) * B * h * w * 2 + static_cast<size_t>(B) * c.n_heads * 4);
             if (l.kind == Layer::DOWN) { h /= 2; w /= 2; }
             if (l.kind == Layer::UP) { h *= 2; w *= 2; }
           }

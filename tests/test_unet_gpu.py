@@ -84,3 +84,30 @@ def test_unet_full_batch_vs_oracle():
             diff = (full[lo:lo + 2] - part).abs().max().item()
             assert diff < 1e-4, f"samples {lo}..{lo + 1}: batch-64 vs batch-2 max abs diff {diff}"
     assert torch.isfinite(full).all()
+
+
+@pytest.mark.parametrize("gain", [2.5, 4.0])
+def test_unet_attention_large_logits(gain):
+    """The attention kernel drops its row-maximum pass when the norm bound Q_max K_max of a (sample, head) is
+    small enough to serve as the softmax stabiliser, and falls back to two passes otherwise (attn_tc.cu).
+    Scaling every to_q / to_k weight by `gain` multiplies the logits by gain^2: 2.5 puts the heads around the
+    switch-over, 4.0 beyond it -- both must still match the oracle."""
+    from oracle.unet_oracle import unet_forward
+
+    model = build_unet(512)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("attn1.to_q.weight") or name.endswith("attn1.to_k.weight"):
+                p.mul_(gain)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 2, 128, 128, generator=g)
+    cond = torch.randn(2, 1, 512, generator=g)
+    t = torch.tensor([700, 40], dtype=torch.long)
+    ref = unet_forward(model.state_dict(), oracle_cfg(512), x, t, cond)
+    m = model.cuda()
+    with torch.no_grad():
+        out = m(x.cuda(), t.cuda(), cond.cuda())
+    err, frac = close_report(out, ref)
+    print(f"gain {gain}: max abs err {err:.3e}, within tol {frac:.6f}")
+    assert torch.isfinite(out).all()
+    assert frac == 1.0, f"max abs err {err}, fraction within rtol {RTOL}/atol {ATOL}: {frac}"

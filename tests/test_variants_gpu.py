@@ -9,6 +9,7 @@ rtol 1e-3 / atol 1e-4.
   PF_FF_F8=1      feed-forward GEMMs on f16f8 operands (GeGLU epilogue writing an f16f8 operand)
   PF_CONV_F8_MAX_HW=0  split-bf16 convolutions everywhere
   PF_QKV_FUSED=0  separate q|k and V projection launches instead of the fused OUT_QKV launch
+  PF_ATTN_1PASS=0 attention always computes its row maxima in a first pass (no norm-bound stabiliser)
 """
 import os
 import re
@@ -29,6 +30,7 @@ CASES = [
     {"PF_FF_F8": "1"},
     {"PF_CONV_F8_MAX_HW": "0", "PF_RAW_LN": "1"},
     {"PF_QKV_FUSED": "0"},
+    {"PF_ATTN_1PASS": "0"},
 ]
 
 
