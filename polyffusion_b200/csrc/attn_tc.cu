@@ -22,7 +22,9 @@
 // The softmax warps write P_hi / P_lo of their own 16 keys straight back into the S columns they
 // just read (tcgen05.st), so the P V instruction of K-step ks finds its A slices at S + 16 ks (hi)
 // and S + 16 ks + 8 (lo).  Q is double buffered in TMEM and staged one work item ahead.
-// Measured alternatives that did NOT help (profiles/README.md): eight vs sixteen softmax warps,
+// Measured alternatives that did NOT help (profiles/README.md): fetching the scores of block j + 1 while the P
+// stores of block j drain (268 vs 228-243 us: publishing P_j later costs more than the overlapped load buys),
+// eight vs sixteen softmax warps,
 // three S accumulators with P in shared memory, four unstacked S/P buffers in TMEM -- the kernel
 // stays at ~290-305 us for N = Nk = 1024 at batch 64 (47 % tensor-pipe active): with ~230 warp
 // instructions per warp per key block the four schedulers are ~50 % busy issuing the softmax itself.
