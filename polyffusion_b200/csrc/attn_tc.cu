@@ -46,6 +46,10 @@ constexpr int AT_OFF_V = AT_OFF_K + AT_KS * 2 * AT_KV_BYTES;  // [VS][hi, lo]
 constexpr int AT_OFF_X = AT_OFF_V + AT_VS * 2 * AT_KV_BYTES;  // float xch[3][128][4]: row maxima, row sums (x2)
 constexpr int AT_SMEM = AT_OFF_X + 3 * 128 * 4 * 4;
 constexpr int AT_SB = 2;  // S/P buffers (key blocks in flight)
+#ifndef PF_ATTN_GROUPS
+#define PF_ATTN_GROUPS 1
+#endif
+constexpr bool AT_GROUPS = PF_ATTN_GROUPS != 0;  // two softmax groups of eight warps (one per S/P buffer)
 constexpr uint32_t TM_O = 0, TM_S = 128, TM_Q = 384;
 
 int attn_smem_bytes() { return AT_SMEM + 1024; }
@@ -66,6 +70,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                :
                : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -299,36 +306,45 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_tc_kernel(const __grid_c
         const float m = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
         mc = m * c;
       }
-      // ---- pass 2: probabilities -> P (TMEM, over the S columns just read), row sums
+      // ---- pass 2: probabilities -> P (TMEM, over the S columns just read), row sums.
+      // The sixteen warps work as TWO groups of eight, one per S/P buffer: group g takes the key blocks that
+      // land in buffer g and each of its warps converts 32 of the block's 64 columns (two 16-column halves), so
+      // two key blocks are in the softmax at any time and one group's TMEM / barrier latencies overlap the other
+      // group's arithmetic (all sixteen warps on one block ran in lockstep).  Each warp arrives with count 2.
       float sum = 0.f;
+      const uint32_t grp = static_cast<uint32_t>(part >> 1), sub = static_cast<uint32_t>(part & 1);
       for (int j = 0; j < nb; ++j, ++sc) {
         const uint32_t sb = sc % AT_SB, sph = (sc / AT_SB) & 1u;
+        if (AT_GROUPS && sb != grp) continue;
         mbar_wait(smem_u32(&s_full[sb]), sph);
         tc_fence_after();
-        const uint32_t sbuf = lane_addr + TM_S + sb * 128 + part * 16;
-        uint32_t v[16], v2[16];
-        tmem_ld16(sbuf, v);
-        tmem_ld16(sbuf + 64, v2);
-        tmem_ld_wait();
-        uint32_t ph[8], pl[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float s0 = __uint_as_float(v[2 * i]) + __uint_as_float(v2[2 * i]);
-          const float s1 = __uint_as_float(v[2 * i + 1]) + __uint_as_float(v2[2 * i + 1]);
-          const float p0 = fast_ex2(fmaf(s0, c, -mc));
-          const float p1 = fast_ex2(fmaf(s1, c, -mc));
-          sum += p0 + p1;
-          split2(p0, p1, ph[i], pl[i]);
+        for (int hf = 0; hf < (AT_GROUPS ? 2 : 1); ++hf) {
+          const uint32_t sbuf = lane_addr + TM_S + sb * 128 + (AT_GROUPS ? sub * 2 + hf : static_cast<uint32_t>(part)) * 16;
+          uint32_t v[16], v2[16];
+          tmem_ld16(sbuf, v);
+          tmem_ld16(sbuf + 64, v2);
+          tmem_ld_wait();
+          uint32_t ph[8], pl[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float s0 = __uint_as_float(v[2 * i]) + __uint_as_float(v2[2 * i]);
+            const float s1 = __uint_as_float(v[2 * i + 1]) + __uint_as_float(v2[2 * i + 1]);
+            const float p0 = fast_ex2(fmaf(s0, c, -mc));
+            const float p1 = fast_ex2(fmaf(s1, c, -mc));
+            sum += p0 + p1;
+            split2(p0, p1, ph[i], pl[i]);
+          }
+          // these 16 S columns become P_hi (8 columns) | P_lo (8 columns)
+          tmem_st8(sbuf, ph);
+          tmem_st8(sbuf + 8, pl);
         }
-        // this warp's own 16 S columns become P_hi (8 columns) | P_lo (8 columns)
-        tmem_st8(sbuf, ph);
-        tmem_st8(sbuf + 8, pl);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(smem_u32(&s_empty[sb]));
-          mbar_arrive(smem_u32(&p_full[sb]));  // P_j lives in S buffer sb
+          mbar_arrive_n(smem_u32(&s_empty[sb]), AT_GROUPS ? 2 : 1);
+          mbar_arrive_n(smem_u32(&p_full[sb]), AT_GROUPS ? 2 : 1);  // P_j lives in S buffer sb
         }
       }
       // the row sums alternate between two exchange buffers: without pass 1 there is only ONE block barrier per

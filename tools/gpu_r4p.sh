@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-4 call P: attention without the row-maximum pass (norm-bound stabiliser): parity, A/B
-tag=${1:-r4p}
+tag=${1:-r4r}
 out=gpurun_out/$tag
 mkdir -p $out
 timeout 600 python -m pytest tests/test_unet_gpu.py tests/test_ops_gpu.py tests/test_samplers_gpu.py -x -q > $out/tests.log 2>&1; echo "tests rc=$?"; tail -3 $out/tests.log
