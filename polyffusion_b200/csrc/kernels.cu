@@ -232,31 +232,47 @@ __global__ void __launch_bounds__(512) gn_finalize_kernel(const double* __restri
                                                           float* __restrict__ shift) {
   pdl_wait();
   pdl_trigger();
+  // same structure as the operand transform's prologue: every thread fetches its own channel's sums (one L2 round
+  // trip), one thread per group reduces from shared memory in channel order, one thread per channel writes
+  __shared__ double2 s_st[512];
+  __shared__ float s_gmean[32], s_grstd[32];
   const int b = blockIdx.x;
   const int cpg = C / groups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
+  const int c = threadIdx.x;  // blockDim.x == C <= 512
+  float gam = 0.f, bet = 0.f;
+  if (c < C) {
+    gam = __ldg(gamma + c);
+    bet = __ldg(beta + c);
+    s_st[c] = __ldcg(reinterpret_cast<const double2*>(stats + (static_cast<long long>(b) * C + c) * 2));
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
     double ts = 0.0, tq = 0.0;
     for (int i = 0; i < cpg; ++i) {
-      const double* st = stats + (static_cast<long long>(b) * C + g * cpg + i) * 2;
-      ts += st[0];
-      tq += st[1];
+      const double2 st = s_st[g * cpg + i];
+      ts += st.x;
+      tq += st.y;
     }
     const double n = static_cast<double>(HW) * cpg;
     const double mean = ts / n;
     double var = tq / n - mean * mean;
     if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float sc = gamma[c] * rstd;
+    s_gmean[g] = static_cast<float>(mean);
+    s_grstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  if (c < C) {
+    const int g = c / cpg;
+    const float sc = gam * s_grstd[g];
     scale[static_cast<long long>(b) * C + c] = sc;
-    shift[static_cast<long long>(b) * C + c] = beta[c] - static_cast<float>(mean) * sc;
+    shift[static_cast<long long>(b) * C + c] = bet - s_gmean[g] * sc;
   }
 }
 
 void launch_gn_finalize(const double* stats, const float* gamma, const float* beta, float eps, int groups,
                         int B, int HW, int C, float* scale, float* shift, cudaStream_t s) {
-  launch_pdl(gn_finalize_kernel, dim3(B), dim3(C < 512 ? C : 512), 0, s, stats, gamma, beta, eps, groups, HW,
-             C, scale, shift);
+  launch_pdl(gn_finalize_kernel, dim3(B), dim3(C), 0, s, stats, gamma, beta, eps, groups, HW, C, scale, shift);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -995,7 +995,7 @@ struct Builder {
     const bool ff_f8 = ff_f8_on && pick_gemm(true, 0, true, H, Wd, 2 * Fh, 128, false).two;
     const bool ln_ff = !ff_f8 && raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, 2 * Fh, bn_geglu, false, 4);
     const bool ln_q2 = raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, C, 0, false, 2);
-    const bool raw_gn = raw_gn_on && x.p && raw_variant_ok(false, 0, false, H, Wd, C, 0, true, ln_qkv ? 6 : 0);
+    const bool raw_gn = raw_gn_on && x.p && C <= 512 && raw_variant_ok(false, 0, false, H, Wd, C, 0, true, ln_qkv ? 6 : 0);
     float* t0 = alloc<float>(rows * C);
     float* rs_t0 = ln_qkv ? new_rowstats(rows) : nullptr;  // row statistics of the current residual stream
     {
@@ -1357,14 +1357,17 @@ struct Builder {
       count_block(m->middle);
       for (auto& b : m->output_blocks) count_block(b);
       gn_pool_doubles = doubles;
-      // LayerNorm row statistics: up to 3 per transformer block, [tokens][2] fp32 each
+      // LayerNorm row statistics (only with PF_RAW_LN=1): up to 3 per transformer block, [tokens][2] fp32 each;
+      // q / k norm bounds of the attention kernel: [B][2][heads][2] fp32 per transformer block
+      static const bool ln_rowstats = std::getenv("PF_RAW_LN") && std::atoi(std::getenv("PF_RAW_LN")) != 0;
       size_t rfloats = 0;
       {
         int h = H, w = Wd;
         auto walk = [&](const BlockSpec& b) {
           for (auto& l : b.layers) {
             if (l.kind == Layer::ST)
-              rfloats += static_cast<size_t>(c.tf_layers) * (static_cast<size_t>(3) * B * h * w * 2 + static_cast<size_t>(B) * c.n_heads * 4);
+              rfloats += static_cast<size_t>(c.tf_layers) *
+                         ((ln_rowstats ? static_cast<size_t>(3) * B * h * w * 2 : 0) + static_cast<size_t>(B) * c.n_heads * 4);
             if (l.kind == Layer::DOWN) { h /= 2; w /= 2; }
             if (l.kind == Layer::UP) { h *= 2; w *= 2; }
           }
