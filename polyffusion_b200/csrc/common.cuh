@@ -193,24 +193,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar_local) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_local & PEER_MASK) : "memory");
 }
-// data-carrying variants: release / acquire at CLUSTER scope (generic shared-memory writes of either CTA of
-// the pair -> the leader's MMA thread)
-__device__ __forceinline__ void mbar_arrive_leader_release(uint32_t bar_local) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_local & PEER_MASK)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
+// (cluster-scope release arrive / acquire wait variants were tried for the RAW conversion warps and dropped: both
+// lower to MEMBAR.ALL.GPU; the data hand-off uses fence.proxy.async.shared::cta + a plain remote arrive, gemm_tc.cu)
 __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const void* desc, uint32_t bar_local, int c0,
                                              int c1, int c2, int c3) {
   asm volatile(

@@ -254,12 +254,12 @@ __global__ void __launch_bounds__(512) gn_finalize_kernel(const double* __restri
       ts += st.x;
       tq += st.y;
     }
-    const double n = static_cast<double>(HW) * cpg;
-    const double mean = ts / n;
-    double var = tq / n - mean * mean;
+    const double inv_n = 1.0 / (static_cast<double>(HW) * cpg);
+    const double mean = ts * inv_n;
+    double var = fma(tq, inv_n, -mean * mean);
     if (var < 0.0) var = 0.0;
     s_gmean[g] = static_cast<float>(mean);
-    s_grstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    s_grstd[g] = rsqrtf(static_cast<float>(var) + eps);
   }
   __syncthreads();
   if (c < C) {
@@ -348,12 +348,14 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
         ts += st.x;
         tq += st.y;
       }
-      const double n = static_cast<double>(a.H) * a.W * cpg;
-      const double mean = ts / n;
-      double var = tq / n - mean * mean;
+      // mean and E[x^2] - mean^2 in fp64 (the subtraction cancels), the reciprocal square root in fp32: an fp64
+      // divide + sqrt + divide chain on 32 threads was ~2 us of pure latency per launch
+      const double inv_n = 1.0 / (static_cast<double>(a.H) * a.W * cpg);
+      const double mean = ts * inv_n;
+      double var = fma(tq, inv_n, -mean * mean);
       if (var < 0.0) var = 0.0;
       s_gmean[g] = static_cast<float>(mean);
-      s_grstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+      s_grstd[g] = rsqrtf(static_cast<float>(var) + a.eps);
     }
     __syncthreads();
 #pragma unroll
@@ -441,7 +443,10 @@ void launch_act_split(const ActSplitArgs& a, cudaStream_t s) {
   // transforms (no prologue) are slower that way (86 -> 98 us for the stride-2 planes) and keep one block per
   // 4 items per thread.  PF_ACT_WAVES overrides (0 = never persistent).
   static const int waves = std::getenv("PF_ACT_WAVES") ? std::atoi(std::getenv("PF_ACT_WAVES")) : 1;
-  long long bx = (items + threads * AS_IPT - 1) / (threads * AS_IPT);
+  // PF_ACT_SMALL_IPT=<n>: items per thread on maps of at most 1024 pixels (more, smaller blocks)
+  static const int small_ipt = std::getenv("PF_ACT_SMALL_IPT") ? std::atoi(std::getenv("PF_ACT_SMALL_IPT")) : AS_IPT;
+  const int ipt = (a.H * a.W <= 1024 && small_ipt > 0) ? small_ipt : AS_IPT;
+  long long bx = (items + threads * ipt - 1) / (threads * ipt);
   if (waves > 0 && a.stats0 != nullptr) {
     const long long slots = 148ll * (1024 / threads) * waves;
     const long long per_sample = std::max(1ll, slots / a.B);

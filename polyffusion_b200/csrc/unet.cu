@@ -1839,7 +1839,7 @@ using namespace pf;
 extern "C" {
 
 const char* pf_last_error(void) { return g_err.c_str(); }
-const char* pf_version(void) { return "polyffusion_b200 0.1 (sm_100a, tcgen05 bf16x3)"; }
+const char* pf_version(void) { return "polyffusion_b200 0.2 (sm_100a, tcgen05 f16f8 + bf16x3)"; }
 
 int pf_unet_create(const pf_unet_cfg* cfg, pf_unet** out) {
   return guarded([&] {
