@@ -200,6 +200,60 @@ def make_mask_golden():
     save("mask_autoreg.npz", **out)
 
 
+
+def reference_experiments_class():
+    """``Experiments`` (and the helpers its ``predict`` calls) lifted from inference_sdf.py:121-303 by ast: the module
+    itself cannot be imported here (omegaconf, pretty_midi, lightning, the data pipeline), and its ``predict`` reads
+    the module globals ``args`` and ``device``.  Returns (Experiments, namespace) with those globals set for a CPU
+    DDPM run (``args.ddim = False``, ``args.repaint_n = 1``)."""
+    import ast
+    from types import SimpleNamespace
+    from typing import Optional
+
+    src = open(os.path.join(reference_loader.REFERENCE_ROOT, "inference_sdf.py")).read()
+    ns = {"torch": torch, "np": np, "Optional": Optional, "device": "cpu", "DiffusionSampler": object,
+          "args": SimpleNamespace(ddim=False, ddim_steps=None, repaint_n=1)}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("get_mask", "get_autoreg_data"):
+            exec(compile(ast.Module([node], []), "inference_sdf.py", "exec"), ns)
+        if isinstance(node, ast.ClassDef) and node.name == "Experiments":
+            # only __init__ and predict: the other methods need the data pipeline / MIDI writers
+            node.body = [n for n in node.body if isinstance(n, ast.FunctionDef) and n.name in ("__init__", "predict")]
+            exec(compile(ast.Module([node], []), "inference_sdf.py", "exec"), ns)
+    return ns["Experiments"], ns
+
+
+def make_predict_golden():
+    """The reference's own ``Experiments.predict(autoreg=True)`` (inference_sdf.py:202-283) on the CPU with the
+    reference's SDFSampler / UNetModel: one song of 2 segments -> 3 half-overlapping windows, ``params.n_steps = 2``
+    (t_idx = 1: two reverse steps per window), inpaint type "below", with and without classifier-free guidance."""
+    import contextlib
+    import io
+    from types import SimpleNamespace
+
+    ref = reference_loader.load()
+    torch.set_num_threads(os.cpu_count() or 1)
+    Experiments, ns = reference_experiments_class()
+    torch.manual_seed(0)
+    unet = ref.UNetModel(**KW, d_cond=512).eval()
+    ldm = ref.LatentDiffusion(unet, None, 0.18215, 1000, 0.00085, 0.012)
+    sdf = ref.SDFSampler(ldm)
+    params = SimpleNamespace(out_channels=2, img_h=128, img_w=128, d_cond=512, n_steps=2)
+    exp = Experiments("sdf", params, sdf)
+    g = torch.Generator().manual_seed(71)
+    orig = synthetic_melody(2, 31)
+    mask = ns["get_mask"](orig, "below")
+    cond = torch.randn(2, 1, 512, generator=g)
+    cond_mid = torch.randn(2, 1, 512, generator=g)
+    out = {}
+    for tag, scale, seed in (("plain", 1.0, 61), ("cfg", 2.0, 62)):
+        with Tape(seed), contextlib.redirect_stdout(io.StringIO()):
+            gen = exp.predict(cond, cond_mid, uncond_scale=scale, autoreg=True, orig=orig.clone(), mask=mask.clone())
+        out[f"{tag}_out"] = gen
+        out[f"{tag}_tape_seed"] = seed
+        out[f"{tag}_scale"] = scale
+    save("predict_autoreg.npz", orig=orig, mask=mask, cond=cond, cond_mid=cond_mid, t_idx=params.n_steps - 1, **out)
+
 def reference_utils_function(name):
     """A pure-numpy function lifted from the reference's utils.py by ast (the module imports
     pretty_midi / matplotlib at the top and cannot be imported here)."""
@@ -316,6 +370,10 @@ if __name__ == "__main__":
         os.makedirs(OUT, exist_ok=True)
         make_decode_golden()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "predict":
+        os.makedirs(OUT, exist_ok=True)
+        make_predict_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "encoders":
         os.makedirs(OUT, exist_ok=True)
         make_encoder_golden()
@@ -328,5 +386,6 @@ if __name__ == "__main__":
         main()
         make_mask_golden()
         make_decode_golden()
+        make_predict_golden()
         make_encoder_golden()
         make_legacy_unet_golden()

@@ -42,3 +42,25 @@ class NoiseTape:
 
     def __call__(self, shape):
         return _RANDN(tuple(shape), generator=self.gen)
+
+
+class CudaTape:
+    """Monkeypatch torch.randn / randn_like so the CUDA samplers draw from a CPU-seeded tape (the same tape the
+    golden generator used on the reference: oracle/make_golden.py ``Tape``)."""
+
+    def __init__(self, seed):
+        self.tape = NoiseTape(seed)
+        self._randn, self._randn_like = torch.randn, torch.randn_like
+
+    def __enter__(self):
+        def randn(*size, **kw):
+            if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)):
+                size = tuple(size[0])
+            return self.tape(size).cuda()
+
+        torch.randn = randn
+        torch.randn_like = lambda t, **kw: self.tape(t.shape).cuda()
+        return self
+
+    def __exit__(self, *a):
+        torch.randn, torch.randn_like = self._randn, self._randn_like

@@ -117,3 +117,63 @@ def test_song_batched_autoreg_matches_sequential_oracle():
         err, frac = close_report(got[s], want)
         print(f"song {s}: max abs err {err:.3e}")
         assert frac == 1.0, f"song {s}: max abs err {err}"
+
+
+PREDICT_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "predict_autoreg.npz")
+
+
+def _predict_golden():
+    g = np.load(PREDICT_GOLD)
+    t = {k: torch.from_numpy(g[k]) for k in ("orig", "mask", "cond", "cond_mid")}
+    cases = [(tag, float(g[f"{tag}_scale"]), int(g[f"{tag}_tape_seed"]), torch.from_numpy(g[f"{tag}_out"]))
+             for tag in ("plain", "cfg")]
+    return t, int(g["t_idx"]), cases
+
+
+def test_oracle_predict_matches_the_reference_predict_golden():
+    """tests/golden/predict_autoreg.npz holds the output of the reference's OWN ``Experiments.predict(autoreg=True)``
+    (inference_sdf.py:202-283, lifted by ast and run on the reference's SDFSampler / UNetModel on the CPU by
+    oracle/make_golden.py).  The oracle restatement of the driver must reproduce it with the same noise tape."""
+    from oracle import autoreg_oracle as ao
+    from oracle import sampler_oracle as so
+    from oracle.unet_oracle import unet_forward
+
+    t, t_idx, cases = _predict_golden()
+    sd = build_unet(512).state_dict()
+    _, beta, alpha_bar = so.ldm_schedule()
+    tb = so.ddpm_tables(alpha_bar, beta)
+    eps_fn = lambda x, tt, c: unet_forward(sd, oracle_cfg(512), x, tt, c)
+    qs = lambda o, ti, n: tb["sqrt_ab"][ti] * o + tb["sqrt_1m_ab"][ti] * n
+    uncond = -torch.ones(1, 1, 512)
+    for tag, scale, seed, want in cases:
+        tape = NoiseTape(seed)
+        noise = tape(tuple(t["orig"].shape))  # predict draws the q_sample noise first (inference_sdf.py:225)
+        paint = lambda xt, c, ti, o, m: so.ddpm_paint(alpha_bar, beta, eps_fn, xt, c, ti, tape, orig=o, mask=m,
+                                                      uncond_scale=scale, uncond_cond=uncond)
+        got = ao.predict_autoreg(paint, qs, t["cond"], t["cond_mid"], t["orig"], t["mask"], noise, t_idx)
+        err = (got - want).abs().max().item()
+        print(f"{tag}: oracle vs reference predict max abs err {err:.3e}")
+        assert got.shape == want.shape and err < 2e-5, (tag, err)
+
+
+@pytest.mark.gpu
+def test_gpu_autoreg_paint_matches_the_reference_predict_golden():
+    """The CUDA drop-in driven the way the reference drives it -- one song, sequential half-overlapping windows,
+    torch.randn in the reference's order -- against the reference's own ``Experiments.predict`` output."""
+    from _util import CudaTape
+    from polyffusion_b200.autoreg import autoreg_paint
+    from polyffusion_b200.sampler_sdf import SDFSampler
+    from polyffusion_b200.stable_diffusion.latent_diffusion import LatentDiffusion
+
+    t, t_idx, cases = _predict_golden()
+    ldm = LatentDiffusion(build_unet(512), None, 0.18215, 1000, 0.00085, 0.012).cuda()
+    sampler = SDFSampler(ldm)
+    uncond = -torch.ones(2, 1, 512).cuda()
+    for tag, scale, seed, want in cases:
+        with CudaTape(seed):
+            got = autoreg_paint(sampler, t["cond"].cuda(), t["cond_mid"].cuda(), t_idx, seg_per_song=2,
+                                orig=t["orig"].cuda(), mask=t["mask"].cuda(), uncond_scale=scale,
+                                uncond_cond=uncond)
+        err, frac = close_report(got[0], want)
+        print(f"{tag}: CUDA autoreg_paint vs reference predict max abs err {err:.3e}, within tol {frac:.6f}")
+        assert got.shape[1:] == want.shape and frac == 1.0, (tag, err, frac)
