@@ -275,9 +275,14 @@ def run_gpu_arm(args):
             # n iterations of SDFSampler.paint's loop body (sampler_sdf.py:313-336): known-region noise, UNet
             # evaluation(s), CFG / x0 / mean / noise / RePaint-blend epilogue.  start stays >= n so that no
             # slice reaches step 0 (which draws no noise)
-            start = n + start % (DDPM_STEPS - n)
-            return sampler.advance(xx, cond, start, n, orig=orig, mask=mask, uncond_scale=cfg["scale"],
-                                   uncond_cond=uncond)
+            # (--steps >= 1000 runs whole 1000-step chains, step 0 included)
+            while n > 0:
+                k = min(n, DDPM_STEPS)
+                s = DDPM_STEPS - 1 if k == DDPM_STEPS else k + start % (DDPM_STEPS - k)
+                xx = sampler.advance(xx, cond, s, k, orig=orig, mask=mask, uncond_scale=cfg["scale"],
+                                     uncond_cond=uncond)
+                n -= k
+            return xx
     # in-kernel Philox noise keyed by the GLOBAL sample index: the sharded run reproduces the 1-GPU samples
     sampler.noise = noise_mode
     sampler.seed = 20261017
