@@ -951,7 +951,8 @@ static GemmKernel pick_raw(int bn, int kind, int v) {
       default: return nullptr;
     }
   }
-  if (kind == 1 && bn == 256) return v == 4 ? gemm_tc2_raw_kernel<256, OUT_GEGLU, 0> : nullptr;
+  if (kind == 1 && bn == 256)
+    return v == 4 ? gemm_tc2_raw_kernel<256, OUT_GEGLU, 0> : v == 0 ? gemm_tc2_raw_kernel<256, OUT_F32, 0> : nullptr;
   if (kind == 5 && bn == 64) return v == 1 ? gemm_tc2fh_raw_kernel<64, 1> : v == 0 ? gemm_tc2fh_raw_kernel<64, 0> : nullptr;
   if (kind == 4 && bn == 64) return v == 1 ? gemm_tc2f_raw_kernel<64, OUT_F32, 1> : nullptr;
   if (kind == 4 && bn == 128) {

@@ -995,7 +995,11 @@ struct Builder {
     const bool ff_f8 = ff_f8_on && pick_gemm(true, 0, true, H, Wd, 2 * Fh, 128, false).two;
     const bool ln_ff = !ff_f8 && raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, 2 * Fh, bn_geglu, false, 4);
     const bool ln_q2 = raw_ln_on && raw_variant_ok(false, 0, false, H, Wd, C, 0, false, 2);
-    const bool raw_gn = raw_gn_on && x.p && C <= 512 && raw_variant_ok(false, 0, false, H, Wd, C, 0, true, ln_qkv ? 6 : 0);
+    // one 256-wide tile per row block: every A tile is converted once instead of twice (50 vs 64 us per launch at
+    // 32 x 32, 23 vs 27 us at 16 x 16, profiles/r4gnbn_*); PF_RAW_GN_BN=128 restores 128-wide stacked tiles
+    static const int raw_gn_bn = std::getenv("PF_RAW_GN_BN") ? std::atoi(std::getenv("PF_RAW_GN_BN")) : 256;
+    const int gn_bn = (raw_gn_bn == 256 && C % 256 == 0 && !ln_qkv) ? 256 : 0;
+    const bool raw_gn = raw_gn_on && x.p && C <= 512 && raw_variant_ok(false, 0, false, H, Wd, C, gn_bn, true, ln_qkv ? 6 : 0);
     float* t0 = alloc<float>(rows * C);
     float* rs_t0 = ln_qkv ? new_rowstats(rows) : nullptr;  // row statistics of the current residual stream
     {
@@ -1015,7 +1019,7 @@ struct Builder {
         ASrc s{Split(), C, Wd, H, B, 0};
         s.raw0 = x.p;
         s.scale = sc; s.shift = sh; s.raw_ld = C;
-        Op& op = conv_gemm(s, w, nullptr, nullptr, H, Wd, C);
+        Op& op = conv_gemm(s, w, nullptr, nullptr, H, Wd, C, 0, gn_bn);
         out_f32(op, t0, C, F(m, L.name + ".proj_in.bias"), 0, nullptr, 0);
         op.g.rowstats = rs_t0;
         afree(sc);
