@@ -10,6 +10,7 @@ rtol 1e-3 / atol 1e-4.
   PF_CONV_F8_MAX_HW=0  split-bf16 convolutions everywhere
   PF_QKV_FUSED=0  separate q|k and V projection launches instead of the fused OUT_QKV launch
   PF_ATTN_1PASS=0 attention always computes its row maxima in a first pass (no norm-bound stabiliser)
+  PF_RAW_GN_BN=128 GroupNorm -> proj_in RAW segment on 128-wide stacked tiles (default: 256-wide)
 """
 import os
 import re
@@ -31,6 +32,7 @@ CASES = [
     {"PF_CONV_F8_MAX_HW": "0", "PF_RAW_LN": "1"},
     {"PF_QKV_FUSED": "0"},
     {"PF_ATTN_1PASS": "0"},
+    {"PF_RAW_GN_BN": "128"},
 ]
 
 
